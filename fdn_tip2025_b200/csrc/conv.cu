@@ -1,0 +1,290 @@
+// Spatial convolutions of the hot path, fp32 FFMA:
+//   dense KxK (3x3 s1/s2, 7x7 s2, strided 1x1) with bias / activation / residual / sigmoid-head epilogues
+//       FDformer patch_embed, output, Downsample/Upsample convs   FDN_arch.py:704, 804, 720, 731
+//       MAR f3_down/f2_down, FAM.merge2, ConvsOut, out, fourier_out FDN_arch.py:192-196, 57, 135, 241-255
+//       FCAFFN conv3_{mul,add}(conv1_{mul,add}(img)) folded into one 3->C 3x3 conv   FDN_arch.py:423
+//       LPNet convs with BatchNorm folded                           LPNet_arch.py:46-61, 90-97
+//   ConvTranspose2d 4x4 stride 2 pad 1 + LeakyReLU                  FDN_arch.py:21-23, 194-195
+//   depthwise 3x3 (plain, +GELU, or C->2C with the GELU gate)       FDN_arch.py:426-427, 435-441, 448, 472-473, 563
+#include "fdn_common.cuh"
+
+struct ConvParams {
+    const float* in;      // [B][Cin][Hin][Win]
+    const float* w;       // [Cout][Cin][K][K]
+    const float* bias;    // [Cout] or null
+    const float* res;     // residual, element (b,co,y,x) at res[((b*Cout+co)*Hr + (y<<res_shift))*Wr + (x<<res_shift)], or null
+    float* out;           // [B][Cout][Hout][Wout]
+    int B, Cin, Cout, Hin, Win, Hout, Wout;
+    int pad;
+    int act;              // 0 none, 1 LeakyReLU(0.1), 2 ReLU   (applied to conv+bias)
+    int head;             // 0: y = act(conv+bias) + res ; 1: y = sigmoid(conv + bias + res) + 1e-8
+    int res_shift, Hr, Wr;
+    int cc;               // input channels staged per iteration
+};
+
+#define CV_TX 16   // threads along x, 4 outputs each
+#define CV_TY 16   // threads along y
+#define CV_NO 8    // output channels per CTA
+
+template <int K, int S>
+__global__ void __launch_bounds__(256) k_conv2d(ConvParams q) {
+    FDN_DYN_SMEM(smem);
+    constexpr int TW = CV_TX * 4, TH = CV_TY;                 // output tile
+    constexpr int IW = (TW - 1) * S + K, IH = (TH - 1) * S + K;   // input tile
+    float* Ws = reinterpret_cast<float*>(smem);               // [cc][K][K][CV_NO]  (first: keeps float4 reads aligned)
+    float* Is = Ws + q.cc * K * K * CV_NO;                    // [cc][IH][IW]
+    const int tid = threadIdx.x, tx = tid % CV_TX, ty = tid / CV_TX;
+    const int tiles_x = (q.Wout + TW - 1) / TW;
+    const int ox0 = (blockIdx.x % tiles_x) * TW, oy0 = (blockIdx.x / tiles_x) * TH;
+    const int co0 = blockIdx.y * CV_NO, b = blockIdx.z;
+    const int ix0 = ox0 * S - q.pad, iy0 = oy0 * S - q.pad;
+    float acc[CV_NO][4];
+#pragma unroll
+    for (int o = 0; o < CV_NO; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[o][j] = 0.f;
+
+    for (int c0 = 0; c0 < q.Cin; c0 += q.cc) {
+        const int nc = min(q.cc, q.Cin - c0);
+        for (int i = tid; i < nc * IH * IW; i += 256) {
+            int c = i / (IH * IW), r = i - c * (IH * IW);
+            int yy = r / IW, xx = r - yy * IW;
+            int gy = iy0 + yy, gx = ix0 + xx;
+            float v = 0.f;
+            if (gy >= 0 && gy < q.Hin && gx >= 0 && gx < q.Win)
+                v = q.in[(((size_t)b * q.Cin + c0 + c) * q.Hin + gy) * q.Win + gx];
+            Is[i] = v;
+        }
+        for (int i = tid; i < nc * K * K * CV_NO; i += 256) {
+            int o = i % CV_NO, r = i / CV_NO;
+            int kk = r % (K * K), c = r / (K * K);
+            int co = co0 + o;
+            Ws[i] = co < q.Cout ? q.w[((size_t)co * q.Cin + c0 + c) * K * K + kk] : 0.f;
+        }
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+            const float* ip = Is + c * IH * IW + (ty * S) * IW + (tx * 4) * S;
+            const float* wp = Ws + c * K * K * CV_NO;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    float4 w0 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * CV_NO);
+                    float4 w1 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * CV_NO + 4);
+                    float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float xv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xv[j] = ip[ky * IW + j * S + kx];
+#pragma unroll
+                    for (int o = 0; o < CV_NO; ++o)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[o][j] += wv[o] * xv[j];
+                }
+        }
+        __syncthreads();
+    }
+    const int oy = oy0 + ty;
+    if (oy >= q.Hout) return;
+#pragma unroll
+    for (int o = 0; o < CV_NO; ++o) {
+        int co = co0 + o;
+        if (co >= q.Cout) continue;
+        float bias = q.bias ? q.bias[co] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int ox = ox0 + tx * 4 + j;
+            if (ox >= q.Wout) continue;
+            float v = acc[o][j] + bias;
+            float r = 0.f;
+            if (q.res) r = q.res[(((size_t)b * q.Cout + co) * q.Hr + ((size_t)oy << q.res_shift)) * q.Wr + ((size_t)ox << q.res_shift)];
+            if (q.head == 1) v = fdn_sigmoid(v + r) + 1e-8f;
+            else v = fdn_act(v, q.act) + r;
+            q.out[(((size_t)b * q.Cout + co) * q.Hout + oy) * q.Wout + ox] = v;
+        }
+    }
+}
+
+// any K / stride: one thread per output element (used for the strided 1x1 convs of LPNet)
+__global__ void k_conv2d_naive(ConvParams q, int K, int S, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int ox = (int)(i % q.Wout);
+    long long t = i / q.Wout;
+    int oy = (int)(t % q.Hout);
+    t /= q.Hout;
+    int co = (int)(t % q.Cout);
+    int b = (int)(t / q.Cout);
+    float acc = q.bias ? q.bias[co] : 0.f;
+    for (int c = 0; c < q.Cin; ++c)
+        for (int ky = 0; ky < K; ++ky) {
+            int gy = oy * S - q.pad + ky;
+            if (gy < 0 || gy >= q.Hin) continue;
+            for (int kx = 0; kx < K; ++kx) {
+                int gx = ox * S - q.pad + kx;
+                if (gx < 0 || gx >= q.Win) continue;
+                acc += q.w[(((size_t)co * q.Cin + c) * K + ky) * K + kx] * q.in[(((size_t)b * q.Cin + c) * q.Hin + gy) * q.Win + gx];
+            }
+        }
+    float r = 0.f;
+    if (q.res) r = q.res[(((size_t)b * q.Cout + co) * q.Hr + ((size_t)oy << q.res_shift)) * q.Wr + ((size_t)ox << q.res_shift)];
+    float v = q.head == 1 ? fdn_sigmoid(acc + r) + 1e-8f : fdn_act(acc, q.act) + r;
+    q.out[i] = v;
+}
+
+template <int K, int S>
+static int launch_conv(ConvParams& q, cudaStream_t st) {
+    constexpr int IW = (CV_TX * 4 - 1) * S + K, IH = (CV_TY - 1) * S + K;
+    size_t per_c = (size_t)(IH * IW + K * K * CV_NO) * sizeof(float);
+    int cc = (int)min((size_t)q.Cin, max((size_t)1, (size_t)(64 * 1024) / per_c));
+    q.cc = cc;
+    size_t smem = per_c * cc;
+    auto kern = k_conv2d<K, S>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
+    }
+    int tiles = fdn_cdiv(q.Wout, CV_TX * 4) * fdn_cdiv(q.Hout, CV_TY);
+    FDN_LAUNCH(kern, dim3(tiles, fdn_cdiv(q.Cout, CV_NO), q.B), dim3(256), smem, st, q);
+    return fdn_check_launch("k_conv2d");
+}
+
+// Dense KxK convolution, groups=1.  y = act(conv(x)+bias) + res           (head = 0)
+//                                   y = sigmoid(conv(x)+bias+res) + 1e-8  (head = 1, MAR illumination heads)
+// res (optional) has spatial size (Hout<<res_shift, Wout<<res_shift) and is sampled at (y<<res_shift, x<<res_shift).
+FDN_API int fdn_conv2d(const float* in, const float* w, const float* bias, const float* res, int res_shift, float* out, int B,
+                       int Cin, int Hin, int Win, int Cout, int K, int stride, int pad, int act, int head, cudaStream_t st) {
+    FDN_REQUIRE(in && w && out && B > 0 && Cin > 0 && Cout > 0 && K > 0 && stride > 0 && pad >= 0, "bad arguments");
+    ConvParams q;
+    q.in = in; q.w = w; q.bias = bias; q.res = res; q.out = out;
+    q.B = B; q.Cin = Cin; q.Cout = Cout; q.Hin = Hin; q.Win = Win;
+    q.Hout = (Hin + 2 * pad - K) / stride + 1;
+    q.Wout = (Win + 2 * pad - K) / stride + 1;
+    FDN_REQUIRE(q.Hout > 0 && q.Wout > 0, "empty output");
+    q.pad = pad; q.act = act; q.head = head; q.res_shift = res_shift;
+    q.Hr = q.Hout << res_shift; q.Wr = q.Wout << res_shift;
+    q.cc = 1;
+    if (K == 3 && stride == 1) return launch_conv<3, 1>(q, st);
+    if (K == 3 && stride == 2) return launch_conv<3, 2>(q, st);
+    if (K == 7 && stride == 2) return launch_conv<7, 2>(q, st);
+    long long total = (long long)B * Cout * q.Hout * q.Wout;
+    FDN_LAUNCH_SEQ(k_conv2d_naive, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, q, K, stride, total);
+    return fdn_check_launch("k_conv2d_naive");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ConvTranspose2d(k=4, s=2, p=1) + LeakyReLU(0.1): out[2H][2W];  w is [Cin][Cout][4][4]
+// out[oy][ox] += in[iy][ix] * w[ky][kx]  with oy = 2*iy - 1 + ky
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_convt4s2(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                           float* __restrict__ out, int Cin, int Cout, int H, int W, int act, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*Cout*2H*2W
+    if (i >= total) return;
+    int Wo = 2 * W, Ho = 2 * H;
+    int ox = (int)(i % Wo);
+    long long t = i / Wo;
+    int oy = (int)(t % Ho);
+    t /= Ho;
+    int co = (int)(t % Cout);
+    int b = (int)(t / Cout);
+    // ky must have the parity of oy+1; two candidates each
+    int ky0 = (oy + 1) & 1, kx0 = (ox + 1) & 1;
+    float acc = bias ? bias[co] : 0.f;
+    for (int c = 0; c < Cin; ++c) {
+        const float* ip = in + ((size_t)b * Cin + c) * H * W;
+        const float* wp = w + ((size_t)c * Cout + co) * 16;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            int ky = ky0 + 2 * a, iy = (oy + 1 - ky) >> 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                int kx = kx0 + 2 * d, ix = (ox + 1 - kx) >> 1;
+                if (ix < 0 || ix >= W) continue;
+                acc += ip[(size_t)iy * W + ix] * wp[ky * 4 + kx];
+            }
+        }
+    }
+    out[i] = fdn_act(acc, act);
+}
+
+FDN_API int fdn_convt4s2(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int H, int W,
+                         int act, cudaStream_t st) {
+    FDN_REQUIRE(in && w && out && B > 0 && Cin > 0 && Cout > 0, "bad arguments");
+    long long total = (long long)B * Cout * H * W * 4;
+    FDN_LAUNCH_SEQ(k_convt4s2, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, in, w, bias, out, Cin, Cout, H, W, act, total);
+    return fdn_check_launch("k_convt4s2");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// depthwise 3x3, zero padding 1.  Each thread produces 4 consecutive pixels of one output channel.
+//   mode 0: out[c] = conv(in[c]; w[c])            mode 1: out[c] = gelu(conv(in[c]; w[c]))
+//   mode 2: gate, w is [2C][9]: out[j] = gelu(conv(in[j/2]; w[j])) * conv(in[(C+j)/2]; w[C+j])
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dw_rows(const float* __restrict__ plane, int H, int W, int y, int x0, float r[3][6]) {
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        int yy = y + dy - 1;
+        bool rowok = yy >= 0 && yy < H;
+        const float* p = plane + (size_t)(rowok ? yy : 0) * W;
+#pragma unroll
+        for (int dx = 0; dx < 6; ++dx) {
+            int xx = x0 + dx - 1;
+            r[dy][dx] = (rowok && xx >= 0 && xx < W) ? p[xx] : 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void dw_apply(const float r[3][6], const float* __restrict__ w, float o[4]) {
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = w[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * r[dy][j + dx];
+        o[j] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dwconv3(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                                                 int C, int H, int W, int mode, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*H*(W/4)
+    if (i >= total) return;
+    int W4 = W >> 2;
+    int x0 = (int)(i % W4) * 4;
+    long long t = i / W4;
+    int y = (int)(t % H);
+    t /= H;
+    int c = (int)(t % C);
+    long long b = t / C;
+    float r[3][6], o[4];
+    if (mode != 2) {
+        dw_rows(in + ((size_t)b * C + c) * H * W, H, W, y, x0, r);
+        dw_apply(r, w + c * 9, o);
+        if (mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fdn_gelu(o[j]);
+        }
+    } else {
+        float o2[4];
+        int ca = c >> 1, cb = (C + c) >> 1;
+        dw_rows(in + ((size_t)b * C + ca) * H * W, H, W, y, x0, r);
+        dw_apply(r, w + c * 9, o);
+        if (cb != ca) dw_rows(in + ((size_t)b * C + cb) * H * W, H, W, y, x0, r);
+        dw_apply(r, w + (C + c) * 9, o2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fdn_gelu(o[j]) * o2[j];
+    }
+    *reinterpret_cast<float4*>(out + (((size_t)b * C + c) * H + y) * W + x0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int C, int H, int W, int mode, cudaStream_t st) {
+    FDN_REQUIRE(in && w && out && B > 0 && C > 0 && H > 0 && W > 0, "bad arguments");
+    FDN_REQUIRE(W % 4 == 0 && fdn_aligned16(out), "W must be a multiple of 4 and out 16-byte aligned");
+    FDN_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
+    long long total = (long long)B * C * H * (W / 4);
+    FDN_LAUNCH_SEQ(k_dwconv3, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, in, w, out, C, H, W, mode, total);
+    return fdn_check_launch("k_dwconv3");
+}

@@ -1,0 +1,58 @@
+// Shared definitions for the libfdn_b200 kernels (sm_100a).
+#pragma once
+
+#ifdef FDN_EMU
+#include "cuda_emu.h"   // tests/emu: host emulation used only for debugging in the GPU-less container
+#define FDN_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#define FDN_LAUNCH(kern, grid, block, smem, stream, ...) \
+    emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); }, true)
+#define FDN_LAUNCH_SEQ(kern, grid, block, smem, stream, ...) \
+    emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); }, false)
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#define FDN_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define FDN_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// kernels that neither synchronise nor shuffle (the emulator may run their threads as a plain loop)
+#define FDN_LAUNCH_SEQ(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <string>
+
+#define FDN_API extern "C" __attribute__((visibility("default")))
+
+// ---- error plumbing (fdn_last_error_string) -------------------------------------------------------
+void fdn_set_error(const std::string& msg);
+int fdn_check_launch(const char* what);   // returns 0 or the cudaError_t of the last launch
+
+#define FDN_REQUIRE(cond, msg)                                                   \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            fdn_set_error(std::string(__func__) + ": " + (msg) + " [" #cond "]"); \
+            return -1;                                                           \
+        }                                                                        \
+    } while (0)
+
+static inline bool fdn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int fdn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- small device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float fdn_gelu(float x) {       // exact erf GELU (F.gelu default)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float fdn_lrelu(float x) { return x > 0.f ? x : 0.1f * x; }
+__device__ __forceinline__ float fdn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// replace_denormals (FDN_arch.py:548-553): |v| < 1e-10 -> +1e-10
+__device__ __forceinline__ float fdn_rd(float v) { return (v < 1e-10f && v > -1e-10f) ? 1e-10f : v; }
+__device__ __forceinline__ float fdn_act(float v, int act) {
+    return act == 1 ? fdn_lrelu(v) : (act == 2 ? fmaxf(v, 0.f) : v);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }

@@ -1,0 +1,597 @@
+// Whole-plane 2-D real FFTs (torch.fft.rfft2 / irfft2, norm='backward') for the global spectral stages:
+// FCAFFN (FDN_arch.py:410-420), MAR FreBlock / fourier_fuse (FDN_arch.py:88-100, 136-148) and the FDN
+// prologue (FDN_arch.py:882-914).
+//
+// Structure (data stays fp32; spectra are float2 [plane][H][W/2+1]):
+//   rows R2C  : real rows -> half spectrum rows                       (k_rows_r2c)
+//   columns   : forward FFT along H on a tile of columns held in shared memory, the per-bin spectral
+//               operator applied in place (FCAFFN modulation / angle / abs), and - for FCAFFN - the
+//               inverse column FFT in the same kernel, so the modulated spectrum never goes to HBM
+//               between the two column passes                          (k_cols)
+//   rows C2R  : Hermitian rows -> real rows, 1/(H*W) scale, residual epilogue (k_rows_c2r)
+// Every 1-D transform is a mixed-radix Stockham autosort FFT in shared memory with register butterflies
+// for radix 2/3/4/5/7/8 and a direct O(p^2) butterfly for any other prime factor (needed by the
+// (H+2)x(W+2) transforms of fourier_fuse: 642 = 2*3*107, 562 = 2*281, ...).  Twiddles come from a
+// per-length table computed in double precision on the host.
+#include "fdn_common.cuh"
+#include "fft8.cuh"
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#define FDN_FFT_MAX_PASSES 16
+
+struct FftPlanDev {
+    int N;
+    int npass;
+    int radix[FDN_FFT_MAX_PASSES];
+    const float2* tw;   // tw[k] = exp(-2 pi i k / N), k in [0, N)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// host: plan cache
+// ---------------------------------------------------------------------------------------------------
+static std::mutex g_plan_mutex;
+static std::map<int, FftPlanDev> g_plans;
+
+static int fdn_fft_get_plan(int N, FftPlanDev* out) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto it = g_plans.find(N);
+    if (it != g_plans.end()) {
+        *out = it->second;
+        return 0;
+    }
+    FftPlanDev p;
+    p.N = N;
+    p.npass = 0;
+    int n = N;
+    const int pref[] = {8, 4, 2, 3, 5, 7};
+    for (int r : pref)
+        while (n % r == 0 && n > 1) {
+            if (p.npass >= FDN_FFT_MAX_PASSES) return -1;
+            p.radix[p.npass++] = r;
+            n /= r;
+        }
+    for (int f = 11; n > 1; f += 2) {
+        if (f * f > n) f = n;
+        while (n % f == 0) {
+            if (p.npass >= FDN_FFT_MAX_PASSES) return -1;
+            p.radix[p.npass++] = f;
+            n /= f;
+        }
+    }
+    std::vector<float2> tw(N);
+    for (int k = 0; k < N; ++k) {
+        // exact values on the axes so purely real paths stay exactly real
+        if ((4LL * k) % N == 0) {
+            int q = (int)((4LL * k) / N);
+            const float c[4] = {1.f, 0.f, -1.f, 0.f}, s[4] = {0.f, -1.f, 0.f, 1.f};
+            tw[k] = make_float2(c[q], s[q]);
+        } else {
+            double a = -2.0 * M_PI * (double)k / (double)N;
+            tw[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    float2* dev = nullptr;
+    if (cudaMalloc((void**)&dev, sizeof(float2) * N) != cudaSuccess) return -2;
+    if (cudaMemcpy(dev, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    p.tw = dev;
+    g_plans[N] = p;
+    *out = p;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device: Stockham passes in shared memory
+// ---------------------------------------------------------------------------------------------------
+template <int SGN>
+__device__ __forceinline__ float2 tw_mul(float2 v, float2 w) {   // v * (SGN<0 ? w : conj(w))
+    return SGN < 0 ? cmul(v, w) : cmulc(v, w);
+}
+
+template <int R> struct Roots;   // cos/sin of 2 pi k / R
+template <> struct Roots<3> {
+    __device__ static __forceinline__ float c(int k) { return k == 0 ? 1.f : -0.5f; }
+    __device__ static __forceinline__ float s(int k) { return k == 0 ? 0.f : (k == 1 ? 0.86602540378443864676f : -0.86602540378443864676f); }
+};
+template <> struct Roots<5> {
+    __device__ static __forceinline__ float c(int k) {
+        return k == 0 ? 1.f : ((k == 1 || k == 4) ? 0.30901699437494742410f : -0.80901699437494742410f);
+    }
+    __device__ static __forceinline__ float s(int k) {
+        return k == 0 ? 0.f : (k == 1 ? 0.95105651629515357212f : (k == 2 ? 0.58778525229247312917f
+                     : (k == 3 ? -0.58778525229247312917f : -0.95105651629515357212f)));
+    }
+};
+template <> struct Roots<7> {
+    __device__ static __forceinline__ float c(int k) {
+        return k == 0 ? 1.f : ((k == 1 || k == 6) ? 0.62348980185873353053f
+                     : ((k == 2 || k == 5) ? -0.22252093395631440429f : -0.90096886790241912624f));
+    }
+    __device__ static __forceinline__ float s(int k) {
+        const float s1 = 0.78183148246802980871f, s2 = 0.97492791218182360702f, s3 = 0.43388373911755812048f;
+        return k == 0 ? 0.f : (k == 1 ? s1 : (k == 2 ? s2 : (k == 3 ? s3 : (k == 4 ? -s3 : (k == 5 ? -s2 : -s1)))));
+    }
+};
+
+template <int R, int SGN>
+__device__ __forceinline__ void butterfly(float2 v[R]) {
+    if constexpr (R == 2) {
+        float2 a = v[0];
+        v[0] = cadd(a, v[1]);
+        v[1] = csub(a, v[1]);
+    } else if constexpr (R == 4) {
+        float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]), a2 = cadd(v[1], v[3]), a3 = csub(v[1], v[3]);
+        float2 ia3 = make_float2(-SGN * a3.y, SGN * a3.x);
+        v[0] = cadd(a0, a2);
+        v[2] = csub(a0, a2);
+        v[1] = cadd(a1, ia3);
+        v[3] = csub(a1, ia3);
+    } else if constexpr (R == 8) {
+        fft8_c2c<SGN>(v);
+    }
+}
+template <int R, int SGN>
+__device__ __forceinline__ void butterfly_direct(float2 v[R]) {   // R in {3,5,7}
+    float2 o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float2 acc = v[0];
+#pragma unroll
+        for (int s = 1; s < R; ++s) {
+            const int k = (r * s) % R;
+            const float wc = Roots<R>::c(k), ws = SGN * Roots<R>::s(k);   // e^{SGN 2 pi i k / R}
+            acc.x += v[s].x * wc - v[s].y * ws;
+            acc.y += v[s].x * ws + v[s].y * wc;
+        }
+        o[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = o[r];
+}
+
+// One radix-R Stockham pass over nseq sequences.  Element n of sequence s lives at s*ss + n*es.
+template <int R, int SGN>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
+                                              int Ns, int nseq, int ss, int es) {
+    const int N = P.N, NR = N / R, M = N / (Ns * R);
+    const int total = nseq * NR;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int seq, j;
+        if (es == 1) { seq = idx / NR; j = idx - seq * NR; } else { j = idx / nseq; seq = idx - j * nseq; }
+        const int k = j % Ns;
+        const float2* src = in + seq * ss;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = src[(j + r * NR) * es];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = tw_mul<SGN>(v[r], P.tw[r * k * M]);
+        }
+        if constexpr (R == 3 || R == 5 || R == 7) butterfly_direct<R, SGN>(v); else butterfly<R, SGN>(v);
+        float2* dst = out + seq * ss;
+        const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[(j0 + r * Ns) * es] = v[r];
+    }
+}
+
+// Any other prime radix: one thread per output element, direct sum over the R inputs.
+template <int SGN>
+__device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
+                                                      int R, int Ns, int nseq, int ss, int es) {
+    const int N = P.N, NR = N / R, M = N / (Ns * R);
+    const int total = nseq * N;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int seq, o;
+        if (es == 1) { seq = idx / N; o = idx - seq * N; } else { o = idx / nseq; seq = idx - o * nseq; }
+        const int k = o % Ns, r = (o / Ns) % R, jhi = o / (Ns * R);
+        const int j = jhi * Ns + k;
+        const int step = (k + r * Ns) * M;     // < N
+        const float2* src = in + seq * ss;
+        float2 acc = make_float2(0.f, 0.f);
+        int t = 0;
+        for (int s = 0; s < R; ++s) {
+            float2 x = src[(j + s * NR) * es];
+            float2 w = P.tw[t];
+            float2 p = tw_mul<SGN>(x, w);
+            acc.x += p.x;
+            acc.y += p.y;
+            t += step;
+            if (t >= N) t -= N;
+        }
+        out[seq * ss + o * es] = acc;
+    }
+}
+
+// Full FFT of nseq sequences; ping-pongs between a and b, returns the buffer holding the result.
+// Must be called by all threads of the block; ends with a __syncthreads().
+template <int SGN>
+__device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq, int ss, int es) {
+    int Ns = 1;
+    for (int p = 0; p < P.npass; ++p) {
+        const int R = P.radix[p];
+        switch (R) {
+            case 2: stockham_pass<2, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            case 3: stockham_pass<3, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            case 4: stockham_pass<4, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            case 5: stockham_pass<5, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            case 7: stockham_pass<7, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            case 8: stockham_pass<8, SGN>(a, b, P, Ns, nseq, ss, es); break;
+            default: stockham_pass_generic<SGN>(a, b, P, R, Ns, nseq, ss, es); break;
+        }
+        __syncthreads();
+        Ns *= R;
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rows: real -> half spectrum
+// ---------------------------------------------------------------------------------------------------
+// in: nrows rows of W floats, row r at in + r*W.  out: row r at out + r*Wf, Wf = W/2+1.
+__global__ void __launch_bounds__(256) k_rows_r2c(const float* __restrict__ in, float2* __restrict__ out, FftPlanDev P,
+                                                  int nrows, int rows_per_cta) {
+    FDN_DYN_SMEM(smem);
+    const int W = P.N, Wf = W / 2 + 1;
+    float2* a = reinterpret_cast<float2*>(smem);
+    float2* b = a + rows_per_cta * W;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int S = min(rows_per_cta, nrows - row0);
+    for (int i = threadIdx.x; i < S * W; i += blockDim.x) a[i] = make_float2(in[(size_t)row0 * W + i], 0.f);
+    __syncthreads();
+    float2* res = fft_smem<-1>(P, a, b, S, W, 1);
+    for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
+        int r = i / Wf, k = i - r * Wf;
+        float2 v = res[r * W + k];
+        if (k == 0 || 2 * k == W) v.y = 0.f;     // exact for real input
+        out[(size_t)(row0 + r) * Wf + k] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rows: half spectrum -> real, with epilogue  out = img_scale[b] * (irfft * norm + res_coef * res)
+// ---------------------------------------------------------------------------------------------------
+struct RowsC2RParams {
+    const float2* in;     // [nrows][Wf]
+    float* out;           // [nrows][W]
+    const float* res;     // [nrows][W] or null
+    const float* img_scale;   // [B] or null
+    float res_coef;
+    float norm;           // 1/(H*W)
+    int nrows;
+    int rows_per_cta;
+    int rows_per_image;   // C*H, to find b for img_scale
+};
+
+__global__ void __launch_bounds__(256) k_rows_c2r(RowsC2RParams q, FftPlanDev P) {
+    FDN_DYN_SMEM(smem);
+    const int W = P.N, Wf = W / 2 + 1;
+    float2* a = reinterpret_cast<float2*>(smem);
+    float2* b = a + q.rows_per_cta * W;
+    const int row0 = blockIdx.x * q.rows_per_cta;
+    const int S = min(q.rows_per_cta, q.nrows - row0);
+    for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
+        int r = i / Wf, k = i - r * Wf;
+        float2 v = q.in[(size_t)(row0 + r) * Wf + k];
+        if (k == 0 || 2 * k == W) {
+            v.y = 0.f;                       // C2R ignores the imaginary part of the DC / Nyquist bins
+            a[r * W + k] = v;
+        } else {
+            a[r * W + k] = v;
+            a[r * W + (W - k)] = make_float2(v.x, -v.y);
+        }
+    }
+    __syncthreads();
+    float2* res = fft_smem<1>(P, a, b, S, W, 1);
+    for (int i = threadIdx.x; i < S * W; i += blockDim.x) {
+        int r = i / W;
+        size_t g = (size_t)row0 * W + i;
+        float v = res[i].x * q.norm;
+        if (q.res) v += q.res_coef * q.res[g];
+        if (q.img_scale) v *= q.img_scale[(row0 + r) / q.rows_per_image];
+        q.out[g] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// columns
+// ---------------------------------------------------------------------------------------------------
+enum { COLS_FWD = 0, COLS_INV = 1, COLS_FWD_MOD_INV = 2, COLS_FWD_ANGLE = 3, COLS_FWD_ABS = 4 };
+
+struct ColsParams {
+    const float2* in;         // spectrum, element (plane, y, x) at in[plane*in_ps + y*in_rs + x]
+    float2* out;              // complex output (modes 0..2)
+    float* out_real;          // real output (modes 3,4), same indexing as out
+    long long in_ps, out_ps;
+    int in_rs, out_rs;
+    int ncols;                // columns to process (W/2+1 of the *output* transform)
+    int W;                    // real width (to locate the Nyquist column), 0 = do not force self-conjugate bins
+    int tc;                   // columns per CTA
+    int mode;
+    // FCAFFN modulation (mode 2): plane = b*C + c
+    int C;
+    const float* amp;         // [B][3][H][ncols]
+    const float* pha;         // [B][3][H][ncols]
+    const float* w_xa;        // [C][3]
+    const float* w_xp;        // [C][3]
+};
+
+__global__ void __launch_bounds__(256) k_cols(ColsParams q, FftPlanDev P) {
+    FDN_DYN_SMEM(smem);
+    const int H = P.N, tc = q.tc;
+    float2* a = reinterpret_cast<float2*>(smem);
+    float2* b = a + H * tc;
+    const int plane = blockIdx.y;
+    const int c0 = blockIdx.x * tc;
+    const int nc = min(tc, q.ncols - c0);
+    const float2* src = q.in + (size_t)plane * q.in_ps + c0;
+    for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+        int y = i / tc, c = i - y * tc;
+        a[i] = c < nc ? src[(size_t)y * q.in_rs + c] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    float2* res;
+    if (q.mode == COLS_INV) {
+        res = fft_smem<1>(P, a, b, tc, 1, tc);
+    } else {
+        res = fft_smem<-1>(P, a, b, tc, 1, tc);
+        float2* other = (res == a) ? b : a;
+        // the four self-conjugate bins of a real signal's spectrum are exactly real
+        if (q.W > 0) {
+            for (int i = threadIdx.x; i < 2 * tc; i += blockDim.x) {
+                int c = i % tc, yy = i / tc;
+                int x = c0 + c;
+                bool xs = (x == 0) || (2 * x == q.W);
+                int y = yy == 0 ? 0 : H / 2;
+                if (xs && (yy == 0 || (H % 2 == 0))) res[y * tc + c].y = 0.f;
+            }
+            __syncthreads();
+        }
+        if (q.mode == COLS_FWD_MOD_INV) {
+            const int bimg = plane / q.C, ch = plane - bimg * q.C;
+            const float a0 = q.w_xa[ch * 3 + 0], a1 = q.w_xa[ch * 3 + 1], a2 = q.w_xa[ch * 3 + 2];
+            const float p0 = q.w_xp[ch * 3 + 0], p1 = q.w_xp[ch * 3 + 1], p2 = q.w_xp[ch * 3 + 2];
+            const size_t mstride = (size_t)H * q.ncols;
+            const float* ampb = q.amp + (size_t)bimg * 3 * mstride + c0;
+            const float* phab = q.pha + (size_t)bimg * 3 * mstride + c0;
+            for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+                int y = i / tc, c = i - y * tc;
+                if (c < nc) {
+                    size_t m = (size_t)y * q.ncols + c;
+                    float A = a0 * ampb[m] + a1 * ampb[m + mstride] + a2 * ampb[m + 2 * mstride];
+                    float Pp = p0 * phab[m] + p1 * phab[m + mstride] + p2 * phab[m + 2 * mstride];
+                    float sn, cs;
+                    sincosf(Pp, &sn, &cs);
+                    float2 z = res[i];
+                    z.x = fdn_rd(z.x);
+                    z.y = fdn_rd(z.y);
+                    // A * z * e^{-iP}
+                    res[i] = make_float2(A * (z.x * cs + z.y * sn), A * (z.y * cs - z.x * sn));
+                }
+            }
+            __syncthreads();
+            res = fft_smem<1>(P, res, other, tc, 1, tc);
+        }
+    }
+    if (q.mode == COLS_FWD_ANGLE || q.mode == COLS_FWD_ABS) {
+        float* dst = q.out_real + (size_t)plane * q.out_ps + c0;
+        for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+            int y = i / tc, c = i - y * tc;
+            if (c < nc) {
+                float2 z = res[i];
+                float v;
+                if (q.mode == COLS_FWD_ANGLE) v = atan2f(fdn_rd(z.y), fdn_rd(z.x));
+                else v = sqrtf(z.x * z.x + z.y * z.y);
+                dst[(size_t)y * q.out_rs + c] = v;
+            }
+        }
+    } else {
+        float2* dst = q.out + (size_t)plane * q.out_ps + c0;
+        for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+            int y = i / tc, c = i - y * tc;
+            if (c < nc) dst[(size_t)y * q.out_rs + c] = res[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MAR per-bin channel MLPs (FreBlock / fourier_fuse): mag, pha -> (1x1, LeakyReLU 0.1, 1x1) each -> polar
+// ---------------------------------------------------------------------------------------------------
+struct SpecMlpParams {
+    float2* spec;             // [B][NC][H*Wf] complex, in place
+    long long plane_stride;   // elements between channels
+    long long nbins;          // H*Wf
+    int B;
+    const float* w;           // packed: W1m[NC*NC] b1m[NC] W2m[NC*NC] b2m[NC] W1p b1p W2p b2p   (row-major [out][in])
+};
+
+template <int NC>
+__global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
+    __shared__ __align__(16) float sw[4 * (NC * NC + NC)];
+    for (int i = threadIdx.x; i < 4 * (NC * NC + NC); i += blockDim.x) sw[i] = q.w[i];
+    __syncthreads();
+    const float* W1m = sw;
+    const float* b1m = W1m + NC * NC;
+    const float* W2m = b1m + NC;
+    const float* b2m = W2m + NC * NC;
+    const float* W1p = b2m + NC;
+    const float* b1p = W1p + NC * NC;
+    const float* W2p = b1p + NC;
+    const float* b2p = W2p + NC * NC;
+    long long bin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int bimg = blockIdx.y;
+    if (bin >= q.nbins) return;
+    float2* z = q.spec + (size_t)bimg * NC * q.plane_stride + bin;
+    float in[NC], hid[NC], om[NC];
+    // magnitude path
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float2 v = z[(size_t)c * q.plane_stride];
+        in[c] = sqrtf(v.x * v.x + v.y * v.y);
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        float acc = b1m[n];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc += W1m[n * NC + k] * in[k];
+        hid[n] = fdn_lrelu(acc);
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        float acc = b2m[n];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc += W2m[n * NC + k] * hid[k];
+        om[n] = acc;
+    }
+    // phase path
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float2 v = z[(size_t)c * q.plane_stride];
+        in[c] = atan2f(v.y, v.x);
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        float acc = b1p[n];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc += W1p[n * NC + k] * in[k];
+        hid[n] = fdn_lrelu(acc);
+    }
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        float acc = b2p[n];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) acc += W2p[n * NC + k] * hid[k];
+        float sn, cs;
+        sincosf(acc, &sn, &cs);
+        z[(size_t)n * q.plane_stride] = make_float2(om[n] * cs, om[n] * sn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+static int rows_per_cta_for(int W) { return max(1, min(8, 4096 / W)); }
+static size_t rows_smem(int W, int rpc) { return (size_t)2 * rpc * W * sizeof(float2); }
+static int cols_per_cta_for(int H) {
+    int tc = 8;
+    while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;
+    return tc;
+}
+
+template <class K>
+static int set_smem(K kern, size_t bytes) {
+    if (bytes > 227 * 1024) {
+        fdn_set_error("FFT tile does not fit in shared memory");
+        return -1;
+    }
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) {
+            fdn_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    return 0;
+}
+
+// Creates (and caches) the twiddle tables for lengths H and W.  Call once per shape before CUDA-graph capture.
+FDN_API int fdn_fft_prepare(int H, int W) {
+    FftPlanDev p;
+    FDN_REQUIRE(H >= 1 && W >= 2, "bad FFT size");
+    FDN_REQUIRE(fdn_fft_get_plan(H, &p) == 0, "plan creation failed");
+    FDN_REQUIRE(fdn_fft_get_plan(W, &p) == 0, "plan creation failed");
+    return 0;
+}
+
+// x [planes][H][W] real -> spec [planes][H][W/2+1] complex (interleaved re,im).  Rows pass only.
+FDN_API int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int W, cudaStream_t st) {
+    FDN_REQUIRE(x && spec && planes > 0 && H > 0 && W >= 2, "bad arguments");
+    FftPlanDev P;
+    FDN_REQUIRE(fdn_fft_get_plan(W, &P) == 0, "plan creation failed");
+    int rpc = rows_per_cta_for(W);
+    size_t smem = rows_smem(W, rpc);
+    int rc = set_smem(k_rows_r2c, smem);
+    if (rc) return rc;
+    int nrows = planes * H;
+    FDN_LAUNCH(k_rows_r2c, dim3(fdn_cdiv(nrows, rpc)), dim3(256), smem, st, x, reinterpret_cast<float2*>(spec), P, nrows, rpc);
+    return fdn_check_launch("k_rows_r2c");
+}
+
+// spec [planes][H][W/2+1] -> y [planes][H][W];  y = img_scale[b] * (irfft_rows(spec)/(norm_hw) + res_coef*res)
+FDN_API int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int W, float inv_norm, const float* res,
+                             float res_coef, const float* img_scale, int planes_per_image, cudaStream_t st) {
+    FDN_REQUIRE(spec && y && planes > 0 && H > 0 && W >= 2, "bad arguments");
+    FftPlanDev P;
+    FDN_REQUIRE(fdn_fft_get_plan(W, &P) == 0, "plan creation failed");
+    RowsC2RParams q;
+    q.in = reinterpret_cast<const float2*>(spec);
+    q.out = y;
+    q.res = res;
+    q.img_scale = img_scale;
+    q.res_coef = res_coef;
+    q.norm = inv_norm;
+    q.nrows = planes * H;
+    q.rows_per_cta = rows_per_cta_for(W);
+    q.rows_per_image = max(1, planes_per_image) * H;
+    size_t smem = rows_smem(W, q.rows_per_cta);
+    int rc = set_smem(k_rows_c2r, smem);
+    if (rc) return rc;
+    FDN_LAUNCH(k_rows_c2r, dim3(fdn_cdiv(q.nrows, q.rows_per_cta)), dim3(256), smem, st, q, P);
+    return fdn_check_launch("k_rows_c2r");
+}
+
+// Column pass over a spectrum.  mode: 0 forward, 1 inverse (unscaled), 2 forward + FCAFFN modulation + inverse,
+// 3 forward -> angle(replace_denormals(.)) real map, 4 forward -> abs real map.
+// in/out are addressed as  base + plane*ps + y*rs + x  (complex elements for spectra, floats for real maps).
+FDN_API int fdn_fft_cols(const float* in, long long in_ps, int in_rs, float* out, long long out_ps, int out_rs, int planes,
+                         int H, int ncols, int W_real, int mode, int C, const float* amp, const float* pha,
+                         const float* w_xa, const float* w_xp, cudaStream_t st) {
+    FDN_REQUIRE(in && out && planes > 0 && H > 0 && ncols > 0, "bad arguments");
+    FDN_REQUIRE(mode >= 0 && mode <= 4, "bad mode");
+    if (mode == COLS_FWD_MOD_INV) FDN_REQUIRE(C > 0 && amp && pha && w_xa && w_xp && planes % C == 0, "modulation needs maps and weights");
+    FftPlanDev P;
+    FDN_REQUIRE(fdn_fft_get_plan(H, &P) == 0, "plan creation failed");
+    ColsParams q;
+    q.in = reinterpret_cast<const float2*>(in);
+    q.out = reinterpret_cast<float2*>(out);
+    q.out_real = out;
+    q.in_ps = in_ps;
+    q.out_ps = out_ps;
+    q.in_rs = in_rs;
+    q.out_rs = out_rs;
+    q.ncols = ncols;
+    q.W = (mode == COLS_INV) ? 0 : W_real;
+    q.tc = cols_per_cta_for(H);
+    q.mode = mode;
+    q.C = C;
+    q.amp = amp;
+    q.pha = pha;
+    q.w_xa = w_xa;
+    q.w_xp = w_xp;
+    size_t smem = (size_t)2 * H * q.tc * sizeof(float2);
+    int rc = set_smem(k_cols, smem);
+    if (rc) return rc;
+    FDN_LAUNCH(k_cols, dim3(fdn_cdiv(ncols, q.tc), planes), dim3(256), smem, st, q, P);
+    return fdn_check_launch("k_cols");
+}
+
+// MAR spectral MLPs in place on spec [B][NC][nbins] complex (channel stride plane_stride complex elements).
+// w = W1m b1m W2m b2m W1p b1p W2p b2p, each W row-major [out][in].
+FDN_API int fdn_spec_mlp(float* spec, long long plane_stride, long long nbins, int B, int NC, const float* w, cudaStream_t st) {
+    FDN_REQUIRE(spec && w && B > 0 && nbins > 0, "bad arguments");
+    SpecMlpParams q;
+    q.spec = reinterpret_cast<float2*>(spec);
+    q.plane_stride = plane_stride;
+    q.nbins = nbins;
+    q.B = B;
+    q.w = w;
+    dim3 grid(fdn_cdiv(nbins, 128), B), block(128);
+    if (NC == 12) { auto k = k_spec_mlp<12>; FDN_LAUNCH(k, grid, block, 0, st, q); }
+    else if (NC == 24) { auto k = k_spec_mlp<24>; FDN_LAUNCH(k, grid, block, 0, st, q); }
+    else if (NC == 48) { auto k = k_spec_mlp<48>; FDN_LAUNCH(k, grid, block, 0, st, q); }
+    else FDN_REQUIRE(false, "unsupported channel count (12/24/48)");
+    return fdn_check_launch("k_spec_mlp");
+}

@@ -1,0 +1,152 @@
+// 8x8-patch spectral operators of the FDformer blocks, one thread per (channel, patch), FFT in registers.
+//   FDFFN spectral branch  FDN_arch.py:458-470   Y = rd(X) * ffta * e^{-i fftp}  (== |rd X| ffta e^{i(angle - fftp)})
+//   FDSA bin algebra       FDN_arch.py:585-630   out1 = |v'| e^{i(th_q - th_k)}, out2 = |rd(qk)| e^{i th_v'},
+//                                                out3 = |rd(qk)| e^{i(th_q - th_k)},  v' = rd(v * fft)
+// The polar forms are evaluated in closed form (no atan2/sincos): e^{i(th_q - th_k)} = (q/|q|) conj(k/|k|) with
+// q, k already passed through replace_denormals, which bounds every modulus away from zero.
+#include "fdn_common.cuh"
+#include "fft8.cuh"
+
+__device__ __forceinline__ void load_patch(const float* __restrict__ base, int W, float p[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        const float4* r = reinterpret_cast<const float4*>(base + (size_t)y * W);
+        float4 a = r[0], b = r[1];
+        p[8 * y + 0] = a.x; p[8 * y + 1] = a.y; p[8 * y + 2] = a.z; p[8 * y + 3] = a.w;
+        p[8 * y + 4] = b.x; p[8 * y + 5] = b.y; p[8 * y + 6] = b.z; p[8 * y + 7] = b.w;
+    }
+}
+__device__ __forceinline__ void store_patch(float* __restrict__ base, int W, const float p[64]) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        float4* r = reinterpret_cast<float4*>(base + (size_t)y * W);
+        r[0] = make_float4(p[8 * y + 0], p[8 * y + 1], p[8 * y + 2], p[8 * y + 3]);
+        r[1] = make_float4(p[8 * y + 4], p[8 * y + 5], p[8 * y + 6], p[8 * y + 7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FDFFN: out = irfft2(rd(rfft2(x)) * wspec[c]) + add
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fdffn_patch(const float* __restrict__ x, const float* __restrict__ add,
+                                                     const float2* __restrict__ wspec, float* __restrict__ out,
+                                                     int C, int H, int W, long long nitems) {
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nitems) return;
+    const int pw = W >> 3, ph = H >> 3;
+    int px = (int)(item % pw);
+    long long t = item / pw;
+    int py = (int)(t % ph);
+    long long plane = t / ph;              // b*C + c
+    int c = (int)(plane % C);
+    size_t off = (size_t)plane * H * W + (size_t)(py * 8) * W + px * 8;
+    float p[64];
+    float2 S[8][5];
+    load_patch(x + off, W, p);
+    rfft2_8x8(p, S);
+    const float2* w = wspec + c * 40;
+#pragma unroll
+    for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            float2 z = make_float2(fdn_rd(S[ky][kx].x), fdn_rd(S[ky][kx].y));
+            S[ky][kx] = cmul(z, w[ky * 5 + kx]);
+        }
+    irfft2_8x8(S, p);
+    if (add) {
+        float q[64];
+        load_patch(add + off, W, q);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) p[i] += q[i];
+    }
+    store_patch(out + off, W, p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FDSA: three lanes (q, k, v roles) cooperate on one (channel, patch); bins are exchanged with shuffles
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fdsa_patch(const float* __restrict__ hid, const float* __restrict__ wfft,
+                                                    float* __restrict__ out, int E, int H, int W, long long nitems) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int t = lane / 3, role = lane - 3 * t;
+    const long long item = warp * 10 + t;
+    const bool valid = (lane < 30) && (item < nitems);
+    const int pw = W >> 3, ph = H >> 3;
+    float p[64];
+    float2 S[8][5];
+    size_t off_out = 0;
+    int e = 0;
+    if (valid) {
+        int px = (int)(item % pw);
+        long long r = item / pw;
+        int py = (int)(r % ph);
+        r /= ph;
+        e = (int)(r % E);
+        long long b = r / E;
+        size_t sp = (size_t)(py * 8) * W + px * 8;
+        load_patch(hid + ((size_t)b * 4 * E + role * E + e) * H * W + sp, W, p);
+        off_out = ((size_t)b * 3 * E + role * E + e) * H * W + sp;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) p[i] = 0.f;
+    }
+    rfft2_8x8(p, S);
+    const int l0 = 3 * t;
+#pragma unroll
+    for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            float wsel = (valid && role == 2) ? wfft[e * 40 + ky * 5 + kx] : 1.0f;
+            float sx = S[ky][kx].x * wsel, sy = S[ky][kx].y * wsel;
+            float2 q = make_float2(__shfl_sync(0xffffffffu, sx, l0), __shfl_sync(0xffffffffu, sy, l0));
+            float2 k = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 1), __shfl_sync(0xffffffffu, sy, l0 + 1));
+            float2 v = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 2), __shfl_sync(0xffffffffu, sy, l0 + 2));
+            // |rd(q k)|
+            float2 qk = cmul(q, k);
+            qk.x = fdn_rd(qk.x);
+            qk.y = fdn_rd(qk.y);
+            float A = sqrtf(qk.x * qk.x + qk.y * qk.y);
+            // unit phasor e^{i(angle rd(q) - angle rd(k))}
+            float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
+            float iq = 1.0f / sqrtf(qc.x * qc.x + qc.y * qc.y), ik = 1.0f / sqrtf(kc.x * kc.x + kc.y * kc.y);
+            float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));
+            // v' = rd(v * fft), m = |v'|
+            float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));
+            float m = sqrtf(vc.x * vc.x + vc.y * vc.y);
+            float2 o;
+            if (role == 0) o = make_float2(m * u.x, m * u.y);                      // |v'| e^{i dtheta}
+            else if (role == 1) { float s = A / m; o = make_float2(s * vc.x, s * vc.y); }   // |qk| e^{i angle v'}
+            else o = make_float2(A * u.x, A * u.y);                                // |qk| e^{i dtheta}
+            S[ky][kx] = o;
+        }
+    irfft2_8x8(S, p);
+    if (valid) store_patch(out + off_out, W, p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+// out = irfft2_8x8( rd(rfft2_8x8(x)) * wspec[c] ) + add.   x, add, out: [B][C][H][W]; wspec: [C][8][5] complex.
+FDN_API int fdn_fdffn_patch(const float* x, const float* add, const float* wspec, float* out, int B, int C, int H, int W,
+                            cudaStream_t st) {
+    FDN_REQUIRE(x && wspec && out && B > 0 && C > 0, "bad arguments");
+    FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
+    FDN_REQUIRE(fdn_aligned16(x) && fdn_aligned16(out) && (!add || fdn_aligned16(add)), "pointers must be 16-byte aligned");
+    long long n = (long long)B * C * (H / 8) * (W / 8);
+    FDN_LAUNCH_SEQ(k_fdffn_patch, dim3(fdn_cdiv(n, 128)), dim3(128), 0, st, x, add, reinterpret_cast<const float2*>(wspec), out, C,
+                   H, W, n);
+    return fdn_check_launch("k_fdffn_patch");
+}
+
+// hid [B][4E][H][W] (q,k,v,v_value groups, after the depthwise 3x3); wfft [E][8][5]; out [B][3E][H][W] = (out1,out2,out3)
+// before their LayerNorms.
+FDN_API int fdn_fdsa_patch(const float* hid, const float* wfft, float* out, int B, int E, int H, int W, cudaStream_t st) {
+    FDN_REQUIRE(hid && wfft && out && B > 0 && E > 0, "bad arguments");
+    FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
+    FDN_REQUIRE(fdn_aligned16(hid) && fdn_aligned16(out), "pointers must be 16-byte aligned");
+    long long n = (long long)B * E * (H / 8) * (W / 8);
+    long long warps = (n + 9) / 10;
+    FDN_LAUNCH(k_fdsa_patch, dim3(fdn_cdiv(warps, 4)), dim3(128), 0, st, hid, wfft, out, E, H, W, n);
+    return fdn_check_launch("k_fdsa_patch");
+}

@@ -1,0 +1,174 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of include/fdn_b200.h).
+
+PyTorch is used for device memory and streams only; every function here launches kernels from
+libfdn_b200.so on ``torch.cuda.current_stream()`` and returns immediately.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _device_ok(t):
+    if not t.is_cuda:
+        raise RuntimeError("fdn_tip2025_b200 runs on CUDA tensors only (got %s); there is no CPU path" % t.device)
+
+
+def _p(t):
+    if t is None:
+        return None
+    _device_ok(t)
+    assert t.dtype == torch.float32 and t.is_contiguous(), "tensors crossing the C ABI are contiguous fp32"
+    return t.data_ptr()
+
+
+def empty(shape, like):
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------ FFT
+def fft_prepare(h, w):
+    _lib.call("fdn_fft_prepare", h, w)
+
+
+def fft_rows_r2c(x, spec):
+    """x [..., H, W] -> spec [..., H, W/2+1, 2]"""
+    h, w = x.shape[-2:]
+    planes = x.numel() // (h * w)
+    _lib.call("fdn_fft_rows_r2c", _p(x), _p(spec), planes, h, w, _stream())
+
+
+def fft_rows_c2r(spec, y, inv_norm, res=None, res_coef=0.0, img_scale=None, planes_per_image=1):
+    h, w = y.shape[-2:]
+    planes = y.numel() // (h * w)
+    _lib.call("fdn_fft_rows_c2r", _p(spec), _p(y), planes, h, w, float(inv_norm), _p(res), float(res_coef), _p(img_scale),
+              planes_per_image, _stream())
+
+
+COLS_FWD, COLS_INV, COLS_FWD_MOD_INV, COLS_FWD_ANGLE, COLS_FWD_ABS = range(5)
+
+
+def fft_cols(src, src_ps, src_rs, dst, dst_ps, dst_rs, planes, h, ncols, w_real, mode, c=0, amp=None, pha=None, w_xa=None,
+             w_xp=None):
+    _lib.call("fdn_fft_cols", _p(src), src_ps, src_rs, _p(dst), dst_ps, dst_rs, planes, h, ncols, w_real, mode, c, _p(amp),
+              _p(pha), _p(w_xa), _p(w_xp), _stream())
+
+
+def spec_mlp(spec, plane_stride, nbins, b, nc, wpack):
+    _lib.call("fdn_spec_mlp", _p(spec), plane_stride, nbins, b, nc, _p(wpack), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ patch spectral
+def fdffn_patch(x, add, wspec, out):
+    b, c, h, w = x.shape
+    _lib.call("fdn_fdffn_patch", _p(x), _p(add), _p(wspec), _p(out), b, c, h, w, _stream())
+
+
+def fdsa_patch(hid, wfft, out):
+    b, c4, h, w = hid.shape
+    _lib.call("fdn_fdsa_patch", _p(hid), _p(wfft), _p(out), b, c4 // 4, h, w, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ per pixel
+def pw_conv(srcs, wt, out, bias=None, ln=None, act=0, film=None, res=None, res_coef=1.0, img_scale=None, out_view=None):
+    """srcs: list of (tensor [B,C,Hs,Ws], shift).  wt [K][N].  out [B,N,H,W] (or out_view=(bs, ps, rs) strides into `out`)."""
+    b = srcs[0][0].shape[0]
+    n = wt.shape[1]
+    if out_view is None:
+        h, w = out.shape[-2:]
+        bs, ps, rs = n * h * w, h * w, w
+    else:
+        h, w, bs, ps, rs = out_view
+    args = []
+    for i in range(3):
+        if i < len(srcs):
+            t, sh = srcs[i]
+            args += [_p(t), t.shape[1], sh]
+        else:
+            args += [None, 0, 0]
+    assert sum(t.shape[1] for t, _ in srcs) == wt.shape[0], "channel count does not match the weight"
+    _lib.call("fdn_pw_conv", *args, _p(wt), _p(bias), _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, act,
+              _p(film[0]) if film else None, _p(film[1]) if film else None, _p(res), float(res_coef), _p(img_scale), _p(out),
+              bs, ps, rs, b, n, h, w, _stream())
+
+
+def chan_ln(x, out, gamma, beta, groups=1, mul=None, mul_bs=0, add=None, add_bs=0):
+    b, gc, h, w = x.shape
+    _lib.call("fdn_chan_ln", _p(x), _p(out), _p(gamma), _p(beta), _p(mul), mul_bs, _p(add), add_bs, b, groups, gc // groups,
+              h * w, _stream())
+
+
+def avgpool2(x, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_avgpool2", _p(x), _p(out), x.numel() // (h * w), h, w, _stream())
+
+
+def up2_bilinear(x, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_up2_bilinear", _p(x), _p(out), x.numel() // (h * w), h, w, _stream())
+
+
+def pixel_unshuffle(x, out, r):
+    b, c, h, w = x.shape
+    _lib.call("fdn_pixel_unshuffle", _p(x), _p(out), b, c, h, w, r, _stream())
+
+
+def gamma_curve(x, illum, out, scale=40.0):
+    _lib.call("fdn_gamma_curve", _p(x), _p(illum), _p(out), float(scale), x.numel(), _stream())
+
+
+def fill_border(t, value, c):
+    h, w = t.shape[-2:]
+    _lib.call("fdn_fill_border", _p(t), _p(value), t.numel() // (h * w), c, h, w, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ spatial convs
+def conv2d(x, w, out, bias=None, res=None, res_shift=0, stride=1, pad=1, act=0, head=0):
+    b, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    _lib.call("fdn_conv2d", _p(x), _p(w), _p(bias), _p(res), res_shift, _p(out), b, cin, h, wd, cout, k, stride, pad, act, head,
+              _stream())
+
+
+def convt4s2(x, w, bias, out, act=1):
+    b, cin, h, wd = x.shape
+    _lib.call("fdn_convt4s2", _p(x), _p(w), _p(bias), _p(out), b, cin, w.shape[1], h, wd, act, _stream())
+
+
+def dwconv3(x, w, out, mode=0):
+    b, c, h, wd = x.shape
+    _lib.call("fdn_dwconv3", _p(x), _p(w), _p(out), b, c, h, wd, mode, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ LPNet
+def avgpool3s2(x, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_avgpool3s2", _p(x), _p(out), x.numel() // (h * w), h, w, _stream())
+
+
+def plane_mean(x, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_plane_mean", _p(x), _p(out), x.numel() // (h * w), h * w, _stream())
+
+
+def se_fc(m, w1, b1, w2, b2, s):
+    b, c = m.shape
+    _lib.call("fdn_se_fc", _p(m), _p(w1), _p(b1), _p(w2), _p(b2), _p(s), b, c, w1.shape[0], _stream())
+
+
+def se_apply(x, s, shortcut, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_se_apply", _p(x), _p(s), _p(shortcut), _p(out), x.numel() // (h * w), h * w, _stream())
+
+
+def lpnet_head(m, w1, b1, w2, b2, gray, out):
+    b, c = m.shape
+    _lib.call("fdn_lpnet_head", _p(m), _p(w1), _p(b1), _p(w2), _p(b2), _p(gray), _p(out), b, c, _stream())
+
+
+def gray_mean(x, out):
+    b, _, h, w = x.shape
+    _lib.call("fdn_gray_mean", _p(x), _p(out), b, h * w, _stream())

@@ -1,0 +1,125 @@
+/* libfdn_b200 - C ABI of the B200 (sm_100a) kernels behind the FDN / FDformer / MAR / LPNet inference forward.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no FFI of its own: the
+ * operators below are what its nn.Module.forward methods call into ATen for.  Each entry point names the reference
+ * lines (under basicsr/models/archs/) whose arithmetic it replaces.  INTEGRATION.md shows the Python (ctypes) stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - all tensors are fp32, contiguous NCHW device memory owned by the caller; spectra are interleaved (re,im) pairs laid
+ *    out [plane][H][W/2+1]; pointers that are read or written with 128-bit accesses must be 16-byte aligned;
+ *  - every call is asynchronous on the caller's stream `st`; the library never synchronises, never allocates per call
+ *    (only fdn_fft_prepare / the first use of an FFT length allocates that length's twiddle table);
+ *  - return 0 = launched; negative = argument error detected on the host before any launch; positive = cudaError_t.
+ *    fdn_last_error_string() describes the last failure on the calling thread.
+ */
+#ifndef FDN_B200_H
+#define FDN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+const char* fdn_last_error_string(void);
+int fdn_abi_version(void);
+int fdn_is_device_build(void);
+
+/* ---- whole-plane FFTs: torch.fft.rfft2 / irfft2(norm='backward')
+ *      FDN_arch.py:90,98 (FreBlock) 139,147 (fourier_fuse) 411,418 (FCAFFN) 882-914 (FDN prologue) -------------------- */
+
+/* Build and cache the twiddle tables for lengths H and W (call before CUDA-graph capture). */
+int fdn_fft_prepare(int H, int W);
+
+/* Row pass R2C: x [planes][H][W] -> spec [planes][H][W/2+1] complex. */
+int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int W, cudaStream_t st);
+
+/* Row pass C2R with epilogue: y = img_scale[b] * (irfft_rows(spec) * inv_norm + res_coef * res).
+ * res and img_scale may be NULL; b = plane / planes_per_image.  (FreBlock "+ x", ProcessBlock "+ xori", "* ratio":
+ * FDN_arch.py:100,118,213-219) */
+int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int W, float inv_norm, const float* res, float res_coef,
+                     const float* img_scale, int planes_per_image, cudaStream_t st);
+
+/* Column pass over ncols columns of length H.  Element (plane,y,x) of in/out lives at base + plane*ps + y*rs + x
+ * (complex elements for spectra, floats for the real maps of modes 3/4).
+ *   mode 0 forward; 1 inverse (unscaled); 2 forward, FCAFFN modulation  Y = rd(X) * A * exp(-iP)  with
+ *   A = sum_j w_xa[c][j] amp[b][j], P = sum_j w_xp[c][j] pha[b][j]  (FDN_arch.py:411-418), inverse - one kernel;
+ *   3 forward then angle(replace_denormals(X)) (FDN_arch.py:882-892); 4 forward then |X| (FDN_arch.py:901-914).
+ * W_real (width of the real signal) locates the Nyquist column so the four self-conjugate bins are made exactly real. */
+int fdn_fft_cols(const float* in, long long in_ps, int in_rs, float* out, long long out_ps, int out_rs, int planes, int H,
+                 int ncols, int W_real, int mode, int C, const float* amp, const float* pha, const float* w_xa,
+                 const float* w_xp, cudaStream_t st);
+
+/* MAR per-bin channel MLPs in place on spec [B][NC][nbins] complex (FDN_arch.py:91-97, 140-146):
+ * mag' = W2m lrelu(W1m |X| + b1m) + b2m, pha' likewise on angle(X), X' = mag' e^{i pha'}.  NC in {12,24,48}.
+ * w packs W1m b1m W2m b2m W1p b1p W2p b2p, matrices row-major [out][in]. */
+int fdn_spec_mlp(float* spec, long long plane_stride, long long nbins, int B, int NC, const float* w, cudaStream_t st);
+
+/* ---- 8x8-patch spectral operators ------------------------------------------------------------------------------------ */
+
+/* FDFFN spectral branch (FDN_arch.py:458-470): out = irfft2_8x8(rd(rfft2_8x8(x)) * wspec[c]) + add, wspec [C][8][5] complex
+ * = ffta * exp(-i fftp).  add may be NULL. */
+int fdn_fdffn_patch(const float* x, const float* add, const float* wspec, float* out, int B, int C, int H, int W, cudaStream_t st);
+
+/* FDSA bin algebra (FDN_arch.py:585-632): hid [B][4E][H][W] = (q,k,v,v_value) after to_hidden_dw; wfft [E][8][5];
+ * out [B][3E][H][W] = (out1,out2,out3) before norm1..3. */
+int fdn_fdsa_patch(const float* hid, const float* wfft, float* out, int B, int E, int H, int W, cudaStream_t st);
+
+/* ---- per-pixel operators ---------------------------------------------------------------------------------------------- */
+
+/* 1x1 convolution over the channel concatenation of up to three sources (nn.Conv2d(k=1), torch.cat, F.interpolate nearest:
+ * FDN_arch.py:55-60,125,168-169,186-191,230-251,388-389,451-452,562,566,685-692).  shift>0: source is 2^shift smaller
+ * (nearest upsample), shift<0: larger (x[::2^-shift]).  wt is the weight transposed to [K][N].  Optional LayerNorm over the
+ * K input channels first (FDN_arch.py:326-342).  Epilogue order: +bias, act (1 LeakyReLU 0.1, 2 ReLU), *film_mul+film_add
+ * (FDN_arch.py:423), +res_coef*res, *img_scale[b].  Output element (b,n,y,x) at out[b*out_bs + n*out_ps + y*out_rs + x]. */
+int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1, int c1, int shift1, const float* src2, int c2,
+                int shift2, const float* wt, const float* bias, const float* ln_w, const float* ln_b, int act,
+                const float* film_mul, const float* film_add, const float* res, float res_coef, const float* img_scale,
+                float* out, long long out_bs, long long out_ps, int out_rs, int B, int N, int H, int W, cudaStream_t st);
+
+/* Grouped channel LayerNorm (FDN_arch.py:326-342, 420, 633-638):
+ * out[b][g*C+c][p] = LN_g(in[b][g*C+c][p]) * mul[b*mul_bs + c*HW + p] + add[b*add_bs + c*HW + p]; mul/add may be NULL. */
+int fdn_chan_ln(const float* in, float* out, const float* gamma, const float* beta, const float* mul, long long mul_bs,
+                const float* add, long long add_bs, int B, int G, int C, int HW, cudaStream_t st);
+
+/* nn.Upsample(0.5, bilinear) == 2x2 mean (FDN_arch.py:265,719,866) and nn.Upsample(2, bilinear, align_corners=False) (:730) */
+int fdn_avgpool2(const float* in, float* out, int planes, int H, int W, cudaStream_t st);
+int fdn_up2_bilinear(const float* in, float* out, int planes, int H, int W, cudaStream_t st);
+/* nn.PixelUnshuffle(r) (FDN_arch.py:199-200) */
+int fdn_pixel_unshuffle(const float* in, float* out, int B, int C, int H, int W, int r, cudaStream_t st);
+/* MAR gamma curve out = 1 - (1-x)^(scale*illum) (FDN_arch.py:282-284) */
+int fdn_gamma_curve(const float* x, const float* illum, float* out, float scale, long long n, cudaStream_t st);
+/* 1-pixel border of t [planes][H][W] <- value[plane % C] (fourier_fuse.fpre[1], padding=1: FDN_arch.py:126) */
+int fdn_fill_border(float* t, const float* value, int planes, int C, int H, int W, cudaStream_t st);
+
+/* ---- spatial convolutions --------------------------------------------------------------------------------------------- */
+
+/* Dense KxK conv, groups=1 (FDN_arch.py:26,57,135,192-196,704,720,731,804; LPNet_arch.py:46-61,90).
+ * head 0: y = act(conv+bias) + res;  head 1: y = sigmoid(conv+bias+res) + 1e-8 (FDN_arch.py:241,248,255).
+ * res is sampled at (y<<res_shift, x<<res_shift) (nearest-downsampled image for the heads). */
+int fdn_conv2d(const float* in, const float* w, const float* bias, const float* res, int res_shift, float* out, int B, int Cin,
+               int Hin, int Win, int Cout, int K, int stride, int pad, int act, int head, cudaStream_t st);
+/* ConvTranspose2d(k=4,s=2,p=1) + activation (FDN_arch.py:21-23,194-195); w [Cin][Cout][4][4] */
+int fdn_convt4s2(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int H, int W, int act,
+                 cudaStream_t st);
+/* Depthwise 3x3, padding 1.  mode 0 plain, 1 +GELU (FDN_arch.py:435-441), 2 C->2C with gelu(x1)*x2 gate, w [2C][9]
+ * (FDN_arch.py:401-402,426-427,448,472-473). */
+int fdn_dwconv3(const float* in, const float* w, float* out, int B, int C, int H, int W, int mode, cudaStream_t st);
+
+/* ---- LPNet (LPNet_arch.py:70-81, 114-134) ------------------------------------------------------------------------------ */
+int fdn_avgpool3s2(const float* in, float* out, int planes, int H, int W, cudaStream_t st);
+int fdn_plane_mean(const float* in, float* out, int planes, int HW, cudaStream_t st);
+int fdn_se_fc(const float* m, const float* w1, const float* b1, const float* w2, const float* b2, float* s, int B, int C, int R,
+              cudaStream_t st);
+int fdn_se_apply(const float* x, const float* s, const float* shortcut, float* out, int planes, int HW, cudaStream_t st);
+int fdn_lpnet_head(const float* m, const float* w1, const float* b1, const float* w2, const float* b2, const float* gray,
+                   float* out, int B, int C, cudaStream_t st);
+int fdn_gray_mean(const float* x, float* out, int B, int HW, cudaStream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDN_B200_H */

@@ -1,0 +1,22 @@
+"""Route the package's C-ABI calls to the host emulation build (tests only; see cuda_emu.h).
+
+Used by tests/test_emu_kernels.py to run the unmodified kernel sources on CPU tensors in the GPU-less build
+container.  Nothing in the product package references this module.
+"""
+import ctypes
+
+_enabled = False
+
+
+def enable():
+    global _enabled
+    from fdn_tip2025_b200 import _lib, build, ops
+    if _enabled:
+        return
+    path = build.build_emu()
+    h = _lib._bind(ctypes.CDLL(path))
+    assert h.fdn_is_device_build() == 0
+    _lib._handle = h
+    ops._stream = lambda: None
+    ops._device_ok = lambda t: None
+    _enabled = True

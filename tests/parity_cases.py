@@ -1,0 +1,305 @@
+"""Parity cases shared by the GPU tests (device='cuda', libfdn_b200.so) and the emulator tests (device='cpu').
+
+Every case runs the product path (fdn_tip2025_b200.ops / archs -> C ABI) and compares with the CPU oracle
+(oracle/fdn_oracle.py, evaluated in float64) or with plain torch float64 for single operators.
+Tolerances follow SURVEY.md section 8(c): block-level rel-L2 <= 1e-5 and max-abs <= 2e-4 * |y|_inf against the
+fp64 oracle; end-to-end (damped weights) max-abs <= 1e-3 and PSNR >= 50 dB.
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from fdn_tip2025_b200 import archs, ops, schema, synth  # noqa: E402
+from oracle import fdn_oracle as O  # noqa: E402
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g, dtype=torch.float64) * 2 - 1) * scale
+
+
+def dev32(t, dev):
+    return t.float().contiguous().to(dev)
+
+
+def sync(dev):
+    if str(dev).startswith("cuda"):
+        torch.cuda.synchronize()
+
+
+def compare(name, got, ref64, rel_l2=1e-5, max_rel=2e-4, report=None):
+    got = got.detach().double().cpu()
+    ref64 = ref64.detach().double().cpu()
+    assert got.shape == ref64.shape, "%s: shape %s vs %s" % (name, tuple(got.shape), tuple(ref64.shape))
+    assert torch.isfinite(got).all(), "%s: non-finite output" % name
+    diff = (got - ref64)
+    l2 = (diff.norm() / ref64.norm().clamp_min(1e-30)).item()
+    mx = (diff.abs().max() / ref64.abs().max().clamp_min(1e-30)).item()
+    if report is not None:
+        report.append((name, l2, mx))
+    assert l2 <= rel_l2 and mx <= max_rel, "%s: rel-L2 %.3e (<= %.1e), max-abs/|y|inf %.3e (<= %.1e)" % (name, l2, rel_l2, mx, max_rel)
+    return l2, mx
+
+
+# ----------------------------------------------------------------------------------------- single operators
+def case_rfft2_irfft2(dev, h, w, planes=3):
+    x = rnd(planes, h, w, seed=h * 1000 + w)
+    x[0] += 3.0     # a strong DC term, as the LayerNorm-ed / image planes have
+    xd = dev32(x, dev)
+    wf = w // 2 + 1
+    spec = torch.empty(planes, h, wf, 2, device=dev)
+    ops.fft_rows_r2c(xd, spec)
+    ops.fft_cols(spec, h * wf, wf, spec, h * wf, wf, planes, h, wf, w, ops.COLS_FWD)
+    sync(dev)
+    ref = torch.fft.rfft2(x.float().double())
+    got = torch.view_as_complex(spec.cpu().contiguous())
+    err = (got.to(torch.complex128) - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-6, "rfft2 %dx%d complex error %.3e" % (h, w, err)
+    # self-conjugate bins exactly real
+    assert got[:, 0, 0].imag.abs().max() == 0
+    if w % 2 == 0:
+        assert got[:, 0, w // 2].imag.abs().max() == 0
+    if h % 2 == 0:
+        assert got[:, h // 2, 0].imag.abs().max() == 0
+    # inverse
+    ops.fft_cols(spec, h * wf, wf, spec, h * wf, wf, planes, h, wf, w, ops.COLS_INV)
+    y = torch.empty(planes, h, w, device=dev)
+    ops.fft_rows_c2r(spec, y, 1.0 / (h * w))
+    sync(dev)
+    compare("irfft2(rfft2) %dx%d" % (h, w), y, x.float().double(), rel_l2=2e-6, max_rel=5e-6)
+
+
+def case_irfft2_nonhermitian(dev, h, w):
+    """irfft2 of an arbitrary (non-Hermitian) half spectrum, as produced by the modulated spectra."""
+    planes = 2
+    wf = w // 2 + 1
+    z = torch.complex(rnd(planes, h, wf, seed=1), rnd(planes, h, wf, seed=2))
+    spec = torch.view_as_real(z.to(torch.complex64)).contiguous().to(dev)
+    ops.fft_cols(spec, h * wf, wf, spec, h * wf, wf, planes, h, wf, w, ops.COLS_INV)
+    y = torch.empty(planes, h, w, device=dev)
+    ops.fft_rows_c2r(spec, y, 1.0 / (h * w))
+    sync(dev)
+    ref = torch.fft.irfft2(z.to(torch.complex64).to(torch.complex128), s=(h, w))
+    compare("irfft2 non-hermitian %dx%d" % (h, w), y, ref, rel_l2=2e-6, max_rel=5e-6)
+
+
+def case_pw_conv(dev):
+    b, h, w = 2, 12, 20
+    # concat of three nearest-resampled sources + bias + lrelu + residual + scale
+    s0, s1, s2 = rnd(b, 5, h, w, seed=1), rnd(b, 7, h // 2, w // 2, seed=2), rnd(b, 3, h * 2, w * 2, seed=3)
+    wgt, bias = rnd(70, 15, seed=4), rnd(70, seed=5)
+    res, scale = rnd(b, 70, h, w, seed=6), rnd(b, seed=7)
+    out = torch.empty(b, 70, h, w, device=dev)
+    ops.pw_conv([(dev32(s0, dev), 0), (dev32(s1, dev), 1), (dev32(s2, dev), -1)], dev32(wgt.t(), dev), out, bias=dev32(bias, dev),
+                act=1, res=dev32(res, dev), res_coef=2.0, img_scale=dev32(scale, dev))
+    sync(dev)
+    cat = torch.cat((s0, s1.repeat_interleave(2, -2).repeat_interleave(2, -1), s2[..., ::2, ::2]), 1).float().double()
+    ref = F.leaky_relu(F.conv2d(cat, wgt.float().double()[:, :, None, None], bias.float().double()), 0.1)
+    ref = (ref + 2.0 * res.float().double()) * scale.float().double().view(b, 1, 1, 1)
+    compare("pw_conv cat/bias/lrelu/res/scale", out, ref, rel_l2=2e-6, max_rel=5e-6)
+    # LayerNorm prologue + FiLM, N <= 32 path, K not a multiple of the chunk
+    x, wgt = rnd(b, 38, h, w, seed=8), rnd(24, 38, seed=9)
+    g, bt = rnd(38, seed=10), rnd(38, seed=11)
+    fm, fa = rnd(b, 24, h, w, seed=12), rnd(b, 24, h, w, seed=13)
+    out = torch.empty(b, 24, h, w, device=dev)
+    ops.pw_conv([(dev32(x, dev), 0)], dev32(wgt.t(), dev), out, ln=(dev32(g, dev), dev32(bt, dev)), film=(dev32(fm, dev), dev32(fa, dev)))
+    sync(dev)
+    xf = x.float().double()
+    mu = xf.mean(1, keepdim=True)
+    var = ((xf - mu) ** 2).mean(1, keepdim=True)
+    ln = (xf - mu) / torch.sqrt(var + 1e-5) * g.float().double().view(1, -1, 1, 1) + bt.float().double().view(1, -1, 1, 1)
+    ref = F.conv2d(ln, wgt.float().double()[:, :, None, None]) * fm.float().double() + fa.float().double()
+    compare("pw_conv ln/film", out, ref, rel_l2=2e-6, max_rel=5e-6)
+
+
+def case_conv2d(dev):
+    b = 2
+    for (cin, cout, k, s, p, hh, ww) in ((5, 11, 3, 1, 1, 20, 70), (12, 24, 3, 2, 1, 18, 22), (3, 16, 7, 2, 3, 40, 36), (6, 9, 1, 6, 0, 25, 31),
+                                         (4, 3, 1, 2, 0, 10, 12)):
+        x, wgt, bias = rnd(b, cin, hh, ww, seed=1), rnd(cout, cin, k, k, seed=2), rnd(cout, seed=3)
+        ho, wo = (hh + 2 * p - k) // s + 1, (ww + 2 * p - k) // s + 1
+        res = rnd(b, cout, ho, wo, seed=4)
+        out = torch.empty(b, cout, ho, wo, device=dev)
+        ops.conv2d(dev32(x, dev), dev32(wgt, dev), out, bias=dev32(bias, dev), res=dev32(res, dev), stride=s, pad=p, act=1)
+        sync(dev)
+        ref = F.leaky_relu(F.conv2d(x.float().double(), wgt.float().double(), bias.float().double(), stride=s, padding=p), 0.1) + res.float().double()
+        compare("conv2d k%d s%d" % (k, s), out, ref, rel_l2=2e-6, max_rel=5e-6)
+    # sigmoid head with a nearest-downsampled residual
+    x, wgt, bias, img = rnd(b, 6, 8, 12, seed=5), rnd(3, 6, 3, 3, seed=6), rnd(3, seed=7), rnd(b, 3, 32, 48, seed=8)
+    out = torch.empty(b, 3, 8, 12, device=dev)
+    ops.conv2d(dev32(x, dev), dev32(wgt, dev), out, bias=dev32(bias, dev), res=dev32(img, dev), res_shift=2, pad=1, head=1)
+    sync(dev)
+    ref = torch.sigmoid(F.conv2d(x.float().double(), wgt.float().double(), bias.float().double(), padding=1) + img.float().double()[..., ::4, ::4]) + 1e-8
+    compare("conv2d sigmoid head", out, ref, rel_l2=2e-6, max_rel=5e-6)
+
+
+def case_convt_dw_misc(dev):
+    b = 2
+    x, wgt, bias = rnd(b, 6, 9, 11, seed=1), rnd(6, 4, 4, 4, seed=2), rnd(4, seed=3)
+    out = torch.empty(b, 4, 18, 22, device=dev)
+    ops.convt4s2(dev32(x, dev), dev32(wgt, dev), dev32(bias, dev), out, act=1)
+    sync(dev)
+    ref = F.leaky_relu(F.conv_transpose2d(x.float().double(), wgt.float().double(), bias.float().double(), stride=2, padding=1), 0.1)
+    compare("convt4s2", out, ref, rel_l2=2e-6, max_rel=5e-6)
+    c = 7
+    x = rnd(b, c, 10, 16, seed=4)
+    for mode in (0, 1):
+        wgt = rnd(c, 1, 3, 3, seed=5)
+        out = torch.empty(b, c, 10, 16, device=dev)
+        ops.dwconv3(dev32(x, dev), dev32(wgt.flatten(1), dev), out, mode=mode)
+        sync(dev)
+        ref = F.conv2d(x.float().double(), wgt.float().double(), padding=1, groups=c)
+        compare("dwconv3 mode %d" % mode, out, F.gelu(ref) if mode else ref, rel_l2=2e-6, max_rel=5e-6)
+    wgt = rnd(2 * c, 1, 3, 3, seed=6)
+    out = torch.empty(b, c, 10, 16, device=dev)
+    ops.dwconv3(dev32(x, dev), dev32(wgt.flatten(1), dev), out, mode=2)
+    sync(dev)
+    r1, r2 = F.conv2d(x.float().double(), wgt.float().double(), padding=1, groups=c).chunk(2, 1)
+    compare("dwconv3 gate", out, F.gelu(r1) * r2, rel_l2=2e-6, max_rel=5e-6)
+    # resampling
+    x = rnd(b, 3, 8, 12, seed=7)
+    out = torch.empty(b, 3, 4, 6, device=dev)
+    ops.avgpool2(dev32(x, dev), out)
+    sync(dev)
+    compare("avgpool2", out, F.interpolate(x.float().double(), scale_factor=0.5, mode="bilinear", align_corners=False), 1e-6, 1e-6)
+    out = torch.empty(b, 3, 16, 24, device=dev)
+    ops.up2_bilinear(dev32(x, dev), out)
+    sync(dev)
+    compare("up2_bilinear", out, F.interpolate(x.float().double(), scale_factor=2, mode="bilinear", align_corners=False), 1e-6, 1e-6)
+    out = torch.empty(b, 48, 2, 3, device=dev)
+    ops.pixel_unshuffle(dev32(x, dev), out, 4)
+    sync(dev)
+    compare("pixel_unshuffle", out, F.pixel_unshuffle(x.float().double(), 4), 1e-7, 1e-7)
+    xx, ii = rnd(500, seed=8).abs() * 0.9, rnd(500, seed=9).abs()
+    out = torch.empty(500, device=dev)
+    ops.gamma_curve(dev32(xx, dev), dev32(ii, dev), out, 40.0)
+    sync(dev)
+    compare("gamma", out, 1 - torch.pow(1 - xx.float().double(), ii.float().double() * 40.0), 2e-6, 5e-6)
+
+
+# ----------------------------------------------------------------------------------------- blocks vs the fp64 oracle
+def _sd64(sd):
+    return O.to_dtype(sd, torch.float64)
+
+
+class _Holder(archs._Net):
+    """A parameter tree for an arbitrary schema table, used to drive single blocks."""
+
+
+def _ctx_for(table, sd, dev):
+    net = _Holder(table)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    return net._context()
+
+
+def case_tblock(dev, dim, h, w, att, light, seed=0, report=None):
+    from collections import OrderedDict
+    table = OrderedDict()
+    schema.transformer_block(table, "blk.", dim, att, light)
+    sd = synth.make_state_dict(table, seed=seed)
+    cx = _ctx_for(table, sd, dev)
+    b = 2
+    x = rnd(b, dim, h, w, seed=seed + 1)
+    wf = w // 2 + 1
+    amp = rnd(b, 3, h, wf, seed=seed + 2).abs() * 3
+    pha = rnd(b, 3, h, wf, seed=seed + 3) * 3.14
+    img = rnd(b, 3, h, w, seed=seed + 4).abs()
+    sd64 = _sd64(sd)
+    f64 = lambda t: t.float().double()
+    side = (dev32(amp, dev), dev32(pha, dev), dev32(img, dev))
+    side64 = (f64(amp), f64(pha), f64(img))
+    xd = dev32(x, dev)
+    if att:
+        got = archs._fdsa(cx, xd, "blk.")
+        sync(dev)
+        ref = f64(x) + O.fdsa(O.layer_norm(f64(x), sd64, "blk.norm1."), sd64, "blk.attn.")
+        compare("FDSA dim %d" % dim, got, ref, report=report)
+    got = archs._fdffn(cx, xd, "blk.")
+    sync(dev)
+    ref = f64(x) + O.fdffn(O.layer_norm(f64(x), sd64, "blk.norm2."), sd64, "blk.ffn.")
+    compare("FDFFN dim %d" % dim, got, ref, report=report)
+    if light:
+        got = archs._fcaffn(cx, xd, side, "blk.")
+        sync(dev)
+        ref = f64(x) + O.fcaffn(O.layer_norm(f64(x), sd64, "blk.norm3."), side64[0], side64[1], side64[2], sd64, "blk.ffn2.")
+        compare("FCAFFN dim %d %dx%d" % (dim, h, w), got, ref, report=report)
+
+
+def case_fuse_resample(dev, n, h, w, report=None):
+    from collections import OrderedDict
+    table = OrderedDict()
+    schema.fuse(table, "fuse.", n)
+    schema._conv(table, "down.body.1.", 2 * n, n, 3, False)
+    schema._conv(table, "up.body.1.", n // 2, n, 3, False)
+    sd = synth.make_state_dict(table, seed=3)
+    cx = _ctx_for(table, sd, dev)
+    sd64 = _sd64(sd)
+    enc, dec = rnd(1, n, h, w, seed=1), rnd(1, n, h, w, seed=2)
+    got = archs._fuse(cx, dev32(enc, dev), dev32(dec, dev), "fuse.")
+    sync(dev)
+    compare("Fuse n=%d" % n, got, O.fuse(enc.float().double(), dec.float().double(), sd64, "fuse."), report=report)
+    got = archs._down(cx, dev32(enc, dev), "down.body.1.weight")
+    sync(dev)
+    compare("Downsample", got, O.conv(O.half(enc.float().double()), sd64, "down.body.1.", padding=1), report=report)
+    got = archs._up(cx, dev32(enc, dev), "up.body.1.weight")
+    sync(dev)
+    compare("Upsample", got, O.conv(O.up2_bilinear(enc.float().double()), sd64, "up.body.1.", padding=1), report=report)
+
+
+def case_mar(dev, h, w, variant, report=None, seed=5):
+    sd = synth.mar_state_dict(seed=seed)
+    net = archs.MAR(variant=variant)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    x = synth.low_light_images(2, h, w)
+    ratio = torch.tensor([[0.3], [0.45]])
+    got = net(x.to(dev), ratio.to(dev))
+    sync(dev)
+    ref = O.mar(x.double(), ratio.double().view(2, 1, 1, 1), _sd64(sd), "", variant)
+    for name, g, r in zip(("1/4", "1/2", "1"), got, ref):
+        compare("MAR[%s] %s %dx%d" % (variant, name, h, w), g, r, rel_l2=2e-4, max_rel=1e-3, report=report)
+
+
+def case_lpnet(dev, h, w, report=None, sd=None):
+    sd = sd if sd is not None else synth.lpnet_state_dict(seed=3)
+    net = archs.I_predict_net()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    x = synth.low_light_images(2, h, w)
+    for ori in (False, True):
+        got = net(x.to(dev), use_ori_i=ori)
+        sync(dev)
+        ref = O.lpnet(x.double(), _sd64(sd), ori)
+        compare("LPNet %dx%d ori=%s" % (h, w, ori), got, ref, rel_l2=1e-5, max_rel=1e-5, report=report)
+
+
+def case_fdn(dev, kind, h, w, b=1, report=None, seed=7):
+    """End-to-end gate with damped weights: max-abs <= 1e-3 and PSNR >= 50 dB vs the fp64 oracle."""
+    dim, variant = (32, "lolblur") if kind == "FDN" else (24, "lolv1")
+    sd = synth.fdn_state_dict(dim=dim, seed=seed, damp=0.03)
+    net = getattr(archs, kind)()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    x = synth.low_light_images(b, h, w)
+    ratio = torch.full((b, 1), 0.35)
+    got = net(x.to(dev), ratio_i=ratio.to(dev))
+    sync(dev)
+    ref = O.fdn(x.double(), ratio.double(), _sd64(sd), variant)
+    out = got[0].double().cpu()
+    mx = (out - ref[0]).abs().max().item()
+    ps = O.psnr(out, ref[0])
+    if report is not None:
+        report.append(("%s %dx%d end-to-end" % (kind, h, w), mx, ps))
+    assert torch.isfinite(out).all()
+    assert mx <= 1e-3 and ps >= 50.0, "%s %dx%d: max-abs %.3e, PSNR %.1f dB" % (kind, h, w, mx, ps)
+    if kind == "FDN":
+        for g, r in zip(got[1:], ref[1:]):
+            assert (g.double().cpu() - r).abs().max().item() <= 1e-3
+    return mx, ps
