@@ -70,9 +70,21 @@ def load():
     return _handle
 
 
+# launch accounting (bench.py reads these; one C-ABI call == one kernel launch, fdn_fft_prepare launches nothing)
+launch_count = 0
+profile_hook = None      # optional callable(name, fn) -> rc used by bench.py to time single launches with CUDA events
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point; non-zero return codes become RuntimeError(fdn_last_error_string())."""
+    global launch_count
     h = load()
-    rc = getattr(h, name)(*args)
+    fn = getattr(h, name)
+    if profile_hook is not None:
+        rc = profile_hook(name, lambda: fn(*args), args)
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, h.fdn_last_error_string().decode()))
+    if name != "fdn_fft_prepare":
+        launch_count += 1

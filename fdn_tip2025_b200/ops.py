@@ -17,11 +17,19 @@ def _device_ok(t):
         raise RuntimeError("fdn_tip2025_b200 runs on CUDA tensors only (got %s); there is no CPU path" % t.device)
 
 
+# bench.py's per-launch accounting: bytes of every tensor operand of the next C-ABI call (each counted once)
+count_bytes = False
+pending_bytes = 0
+
+
 def _p(t):
+    global pending_bytes
     if t is None:
         return None
     _device_ok(t)
     assert t.dtype == torch.float32 and t.is_contiguous(), "tensors crossing the C ABI are contiguous fp32"
+    if count_bytes:
+        pending_bytes += t.numel() * 4
     return t.data_ptr()
 
 

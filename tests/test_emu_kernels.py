@@ -1,0 +1,38 @@
+"""Kernel-source checks on the CUDA-semantics emulator (tests/emu): the same .cu files compiled with g++ and run on
+CPU tensors, compared with torch fp64 / the fp64 oracle.  This is a debugging aid for the GPU-less build container and
+covers host-side index logic; the parity claims are made by tests/test_gpu_parity.py on the B200."""
+import pytest
+
+import parity_cases as P
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu import harness
+    harness.enable()
+    yield "cpu"
+    # restore the product loader so later tests see the real library
+    from fdn_tip2025_b200 import _lib, ops
+    import importlib
+    _lib._handle = None
+    importlib.reload(ops)
+
+
+@pytest.mark.parametrize("h,w", [(8, 8), (16, 24), (30, 14), (13, 22), (34, 26)])
+def test_emu_fft(emu, h, w):
+    P.case_rfft2_irfft2(emu, h, w)
+    P.case_irfft2_nonhermitian(emu, h, w)
+
+
+def test_emu_pointwise_and_convs(emu):
+    P.case_pw_conv(emu)
+    P.case_conv2d(emu)
+    P.case_convt_dw_misc(emu)
+
+
+def test_emu_transformer_block(emu):
+    P.case_tblock(emu, 32, 8, 16, True, True)
+
+
+def test_emu_fuse(emu):
+    P.case_fuse_resample(emu, 32, 8, 8)
