@@ -24,6 +24,9 @@ SIGNATURES = {
     "fdn_fdffn_patch": "ppppiiiis",
     "fdn_fdsa_patch": "pppiiiis",
     "fdn_pw_conv": "piipiipiippppipppfpplliiiiis",
+    "fdn_has_tcgen05": "",
+    "fdn_pw_mma": "pipipiiiippplpppppfpiiis",
+    "fdn_group_stats": "ppiiiis",
     "fdn_chan_ln": "ppppplpliiiis",
     "fdn_avgpool2": "ppiiis",
     "fdn_up2_bilinear": "ppiiis",

@@ -14,7 +14,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops, schema
+from . import ops, packing, schema
 
 __all__ = ["FDN", "FDN_lolv1", "FDformer", "MAR", "I_predict_net"]
 
@@ -106,6 +106,26 @@ class _Ctx:
         """1x1 conv weight [N,K,1,1] -> [K][N]."""
         return self.cached("wt:" + key, lambda: self.sd[key].flatten(1).t())
 
+    def packed(self, key):
+        """1x1 conv weight packed for the tcgen05 kernel: (bpack, N, Nc, nchunks)."""
+        name = "mma:" + key
+        t = self.pack.get(name)
+        if t is None:
+            with torch.no_grad():
+                t = packing.pack_weight(self.sd[key].flatten(1))
+            self.pack[name] = t
+        return t
+
+    def packed_fuse_out(self, p):
+        name = "mma_fuse_out:" + p
+        t = self.pack.get(name)
+        if t is None:
+            wt, bias = self.fuse_out(p)
+            with torch.no_grad():
+                t = packing.pack_weight(wt.t().contiguous())
+            self.pack[name] = t
+        return t
+
     def flat(self, key):
         return self.cached("flat:" + key, lambda: self.sd[key].reshape(self.sd[key].shape[0], -1))
 
@@ -183,21 +203,50 @@ def _new(like, *shape):
 # =====================================================================================================
 # FDformer blocks                                                    (FDN_arch.py:381-475, 556-695)
 # =====================================================================================================
+def _gemm_mode():
+    """'tf32x3' (default: tcgen05 with the 3xTF32 split, fp32-level accuracy), 'tf32' (single-pass TF32, reported
+    separately) or 'ffma' (CUDA-core kernel).  The tensor-core kernel needs the device build of the library."""
+    mode = os.environ.get("FDN_B200_GEMM", "tf32x3")
+    if mode not in ("tf32x3", "tf32", "ffma"):
+        raise RuntimeError("FDN_B200_GEMM must be tf32x3, tf32 or ffma")
+    if mode != "ffma" and not ops.has_tcgen05():
+        return "ffma"
+    return mode
+
+
+def _conv1x1(cx, srcs, key, out, ln=None, bias=None, film=None, res=None):
+    """1x1 convolution of the FDformer blocks: tcgen05 kernel, or the FFMA kernel when FDN_B200_GEMM=ffma."""
+    mode = _gemm_mode()
+    if mode == "ffma":
+        ops.pw_conv([(t, 0) for t in srcs], cx.wt(key), out, bias=bias, ln=ln, film=film, res=res, res_coef=1.0)
+    else:
+        ops.pw_mma(srcs, cx.packed(key), out, prologue=1 if ln else 0, ln=ln, bias=bias, film=film, res=res, res_coef=1.0,
+                   passes=1 if mode == "tf32" else 3)
+
+
 def _fdsa(cx, x, p):
     """x + FDSA(LN1(x)).  p = block prefix."""
     b, c, h, w = x.shape
     e = schema.expand_dim(c)
     hid = _new(x, b, 4 * e, h, w)
-    ops.pw_conv([(x, 0)], cx.wt(p + "attn.to_hidden.weight"), hid, ln=cx.ln(p + "norm1."))
+    _conv1x1(cx, [x], p + "attn.to_hidden.weight", hid, ln=cx.ln(p + "norm1."))
     hid_dw = _new(x, b, 4 * e, h, w)
     ops.dwconv3(hid, cx.flat(p + "attn.to_hidden_dw.weight"), hid_dw, mode=0)
     del hid
     o = _new(x, b, 3 * e, h, w)
     ops.fdsa_patch(hid_dw, cx.flat(p + "attn.fft"), o)
     g3, b3 = cx.ln3(p + "attn.")
-    ops.chan_ln(o, o, g3, b3, groups=3, mul=hid_dw.view(-1)[3 * e * h * w:], mul_bs=4 * e * h * w)
+    vv = hid_dw.view(-1)[3 * e * h * w:]                     # v_value group, batch stride 4E*HW
     out = _new(x, b, c, h, w)
-    ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
+    mode = _gemm_mode()
+    if mode == "ffma":
+        ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=4 * e * h * w)
+        ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
+    else:   # norm1..3, the v_value gate and project_out in one kernel (LayerNorm statistics from a small pre-pass)
+        stats = _new(x, b, 3, 2, h * w)
+        ops.group_stats(o, stats, 3)
+        ops.pw_mma([o], cx.packed(p + "attn.project_out.weight"), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=4 * e * h * w,
+                   stats=stats, res=x, res_coef=1.0, passes=1 if mode == "tf32" else 3)
     return out
 
 
@@ -206,7 +255,7 @@ def _fdffn(cx, x, p):
     b, c, h, w = x.shape
     hd = schema.ffn_hidden(c)
     hid = _new(x, b, hd, h, w)
-    ops.pw_conv([(x, 0)], cx.wt(p + "ffn.project_in.weight"), hid, ln=cx.ln(p + "norm2."))
+    _conv1x1(cx, [x], p + "ffn.project_in.weight", hid, ln=cx.ln(p + "norm2."))
     s1 = _new(x, b, hd, h, w)
     ops.dwconv3(hid, cx.flat(p + "ffn.space.0.weight"), s1, mode=1)
     s2 = _new(x, b, hd, h, w)
@@ -214,7 +263,7 @@ def _fdffn(cx, x, p):
     ops.fdffn_patch(hid, s2, cx.ffn_spec(p + "ffn."), s1)          # s1 <- spectral branch + spatial branch
     ops.dwconv3(s1, cx.flat(p + "ffn.dwconv.weight"), s2, mode=2)  # s2 <- gated
     out = _new(x, b, c, h, w)
-    ops.pw_conv([(s2, 0)], cx.wt(p + "ffn.project_out.weight"), out, res=x, res_coef=1.0)
+    _conv1x1(cx, [s2], p + "ffn.project_out.weight", out, res=x)
     return out
 
 
@@ -233,16 +282,21 @@ def _fcaffn(cx, x, side, p):
     y = _new(x, b, c, h, w)
     ops.fft_rows_c2r(spec, y, 1.0 / (h * w))
     del spec
-    g, bt = cx.ln(p + "ffn2.norm.")
-    ops.chan_ln(y, y, g, bt, mul=x1, mul_bs=c * h * w, add=x1, add_bs=c * h * w)
-    fmul, fadd = _new(x, b, c, h, w), x1                     # x1 is dead after the mix: reuse it for the add map
+    fmul, fadd = _new(x, b, c, h, w), _new(x, b, c, h, w)
     ops.conv2d(img, cx.film(p + "ffn2.", "mul"), fmul, pad=1)
     ops.conv2d(img, cx.film(p + "ffn2.", "add"), fadd, pad=1)
     t = _new(x, b, c, h, w)
-    ops.pw_conv([(y, 0)], cx.wt(p + "ffn2.project_in.weight"), t, film=(fmul, fadd))
+    mode = _gemm_mode()
+    if mode == "ffma":
+        g, bt = cx.ln(p + "ffn2.norm.")
+        ops.chan_ln(y, y, g, bt, mul=x1, mul_bs=c * h * w, add=x1, add_bs=c * h * w)
+        ops.pw_conv([(y, 0)], cx.wt(p + "ffn2.project_in.weight"), t, film=(fmul, fadd))
+    else:   # LN(irfft)*x1 + x1, project_in and the FiLM in one kernel
+        ops.pw_mma([y], cx.packed(p + "ffn2.project_in.weight"), t, prologue=3, ln=cx.ln(p + "ffn2.norm."), aux=x1,
+                   aux_bs=c * h * w, film=(fmul, fadd), passes=1 if mode == "tf32" else 3)
     ops.dwconv3(t, cx.flat(p + "ffn2.dwconv.weight"), y, mode=2)
     out = fmul
-    ops.pw_conv([(y, 0)], cx.wt(p + "ffn2.project_out.weight"), out, res=x, res_coef=1.0)
+    _conv1x1(cx, [y], p + "ffn2.project_out.weight", out, res=x)
     return out
 
 
@@ -266,11 +320,15 @@ def _stage(cx, x, side, p):
 def _fuse(cx, enc, dec, p):
     b, n, h, w = enc.shape
     x = _new(enc, b, 2 * n, h, w)
-    ops.pw_conv([(enc, 0), (dec, 0)], cx.wt(p + "conv.weight"), x, bias=cx.plain(p + "conv.bias"))
+    _conv1x1(cx, [enc, dec], p + "conv.weight", x, bias=cx.plain(p + "conv.bias"))
     x = _tblock(cx, x, None, p + "att_channel.")
     wt, bias = cx.fuse_out(p)
     out = _new(enc, b, n, h, w)
-    ops.pw_conv([(x, 0)], wt, out, bias=bias)
+    mode = _gemm_mode()
+    if mode == "ffma":
+        ops.pw_conv([(x, 0)], wt, out, bias=bias)
+    else:
+        ops.pw_mma([x], cx.packed_fuse_out(p), out, bias=bias, passes=1 if mode == "tf32" else 3)
     return out
 
 

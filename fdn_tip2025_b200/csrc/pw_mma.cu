@@ -1,0 +1,614 @@
+// 1x1 convolutions of the FDformer blocks on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   Y[b, n, p] = epilogue( sum_k W[n, k] * prologue(X)[b, k, p] )       p = pixel, M = 128 pixels per tile
+//
+// These are the only dense contractions of the network (83 % of its FLOPs):
+// FDSA to_hidden / project_out, FDFFN project_in / project_out, FCAFFN project_in / project_out, Fuse conv / conv2
+// (FDN_arch.py:388-389, 451-452, 562, 566, 685-686).
+//
+// Persistent, warp-specialised kernel (18 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
+//   warp  17    loader: streams raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
+//               into a shared-memory ring with cp.async.bulk (TMA bulk copies, 512 contiguous bytes per channel row)
+//               completing on mbarrier transaction counts - several tiles ahead of the consumers, which is what keeps
+//               enough bytes in flight to cover HBM latency
+//   warps 0-7   producers: two threads per pixel; take the LayerNorm statistics from shared memory (two-pass mean /
+//               biased variance like the reference), apply the per-pixel prologue, split each value into tf32 hi + lo
+//               and store it into the canonical K-major SWIZZLE_128B operand stage
+//   warp  16    MMA issuer: one elected lane issues tcgen05.mma (cta_group::1, kind::tf32, 128 x N x 8) with the weight
+//               panel that is resident in shared memory (packed on the host into the UMMA image) and owns TMEM
+//   warps 8-15  epilogue: thread = TMEM lane = pixel (two warps per lane quadrant split the columns); residual prefetched into registers, tcgen05.ld, IEEE sum of the
+//               accumulators, bias / FiLM / residual, 128-byte coalesced NCHW stores
+// Barriers: raw_full[r] (tx bytes) -> producers -> raw_empty[r]; a_full[s] (256 arrivals) -> MMA; tcgen05.commit ->
+// a_empty[s]; commit -> acc_full -> epilogue -> acc_empty (256 arrivals) -> MMA of the next tile.
+//
+// Precision: passes = 3 ("3xTF32", default) splits both operands into tf32 hi + tf32 lo and accumulates
+// hi*hi + hi*lo + lo*hi.  The split itself is exact to 7e-8; because the tensor core truncates its fp32 accumulator after
+// every instruction, the large hi*hi sum and the small corrections live in separate TMEM accumulators and long K is
+// spread round-robin over up to three main accumulators, which the epilogue adds with IEEE fp32 additions.
+// passes = 1 is single-pass TF32 (reported separately).
+#include "fdn_common.cuh"
+
+#ifndef FDN_EMU
+
+#define MMA_TP 128          // pixels per tile (UMMA M)
+#define MMA_KB 32           // channels per K block (one 128-byte swizzle row of tf32)
+#define MMA_PROD_THREADS 256
+#define MMA_EPI_WARP0 8
+#define MMA_EPI_THREADS 256
+#define MMA_MMA_WARP 16
+#define MMA_LOAD_WARP 17
+#define MMA_THREADS 576
+#define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
+#define MMA_MAX_RING 8
+#define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
+
+struct PwMmaParams {
+    const float* src0;      // [B][C0][HW]
+    const float* src1;      // [B][C1][HW] or null (channel concat)
+    int C0, C1;
+    int K;                  // C0 + C1
+    int Kpad;               // K rounded up to 8
+    int N;                  // real output channels
+    int Nc;                 // padded output channels per chunk (multiple of 16, <= 256)
+    int HW, B;
+    const float* bpack;     // [nchunks][kblocks][2 (hi,lo)][Nc][32] floats, pre-swizzled
+    int prologue;           // 0 none, 1 LayerNorm(K), 2 FDSA gate (3 LN groups, stats precomputed) x v_value, 3 FCAFFN mix
+    const float* ln_w;      // [K] (prologue 1,3) or [3][E] (prologue 2)
+    const float* ln_b;
+    const float* aux;       // prologue 2: v_value, element (b,e,p) at aux[b*aux_bs + e*HW + p]; prologue 3: x1 [B][K][HW]
+    long long aux_bs;
+    const float* stats;     // prologue 2: [B][3][2][HW] (mean, 1/sqrt(var+eps)) per LayerNorm group
+    const float* bias;      // [N] or null
+    const float* film_mul;  // [B][N][HW] or null
+    const float* film_add;
+    const float* res;       // [B][N][HW] or null
+    float res_coef;
+    float* out;             // [B][N][HW]
+    int passes;             // 3 = 3xTF32, 1 = TF32
+    uint32_t idesc;
+    int b_resident;         // whole weight chunk kept in shared memory (else streamed into the operand stage)
+    int nstage;             // operand stages (1 or 2)
+    int ring;               // raw ring slots
+    int nmain;              // main accumulators (K blocks round-robin)
+    int tmem_cols;          // power of two >= (nmain + (passes==3)) * Nc
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset (leading byte offset unused: one atom along K)
+    d |= (uint64_t)1 << 46;                          // version
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// byte offset of the 16-byte group `chunk` of row `row` inside a [rows][32 floats] K-major SWIZZLE_128B panel
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ const float* src_row(const PwMmaParams& q, int b, int k) {
+    if (k < q.C0) return q.src0 + ((size_t)b * q.C0 + k) * q.HW;
+    return q.src1 + ((size_t)b * q.C1 + (k - q.C0)) * q.HW;
+}
+
+template <int PRO, int PASSES>
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t a_bytes = MMA_TP * 128;
+    constexpr bool has_aux = PRO >= 2;
+    constexpr uint32_t slot_bytes = MMA_SLOT_BYTES * (has_aux ? 2 : 1) + (PRO == 2 ? 6 * MMA_TP * 4 : 0);
+    const uint32_t b_bytes = (uint32_t)q.Nc * 128;
+    const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
+    const uint32_t bres_bytes = q.b_resident ? (uint32_t)nkb * 2 * b_bytes : 0;
+    const uint32_t stage_bytes = 2 * a_bytes + (q.b_resident ? 0 : 2 * b_bytes);
+    unsigned char* s_bres = smem;
+    unsigned char* s_stage = s_bres + bres_bytes;
+    unsigned char* s_raw = s_stage + q.nstage * stage_bytes;
+    float* s_part = reinterpret_cast<float*>(s_raw + q.ring * slot_bytes);       // [2][128] partial sums
+    float* s_gam = s_part + 2 * MMA_TP;                                          // [MMA_MAX_K] LayerNorm gamma
+    float* s_bet = s_gam + MMA_MAX_K;                                            // [MMA_MAX_K] LayerNorm beta
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(s_bet + MMA_MAX_K);
+    uint64_t* raw_empty = raw_full + MMA_MAX_RING;
+    uint64_t* a_full = raw_empty + MMA_MAX_RING;
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* acc_full = a_empty + 2;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.y;
+    const int HW = q.HW;
+    const int tiles_per_img = (HW + MMA_TP - 1) / MMA_TP;
+    const int ntiles = tiles_per_img * q.B;
+    const float* bsrc = q.bpack + (size_t)chunk * nkb * 2 * q.Nc * 32;
+    constexpr int panels = PASSES == 3 ? 2 : 1;
+    const int gsize = PRO == 2 ? q.K / 3 : q.K;
+
+    if (tid == 0) {
+        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
+        for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS); mbar_init(&a_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, MMA_EPI_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)q.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (PRO != 0)
+        for (int i = tid; i < nkb * MMA_KB; i += MMA_THREADS) {
+            s_gam[i] = i < q.K ? q.ln_w[i] : 0.f;
+            s_bet[i] = i < q.K ? q.ln_b[i] : 0.f;
+        }
+    if (q.b_resident) {      // the whole weight chunk stays in shared memory for the lifetime of the CTA
+        const float4* src = reinterpret_cast<const float4*>(bsrc);
+        float4* dst = reinterpret_cast<float4*>(s_bres);
+        const int per_kb = 2 * q.Nc * 8, used = panels * q.Nc * 8;
+        for (int i = tid; i < nkb * per_kb; i += MMA_THREADS)
+            if ((i % per_kb) < used) dst[i] = src[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const int nmain = q.nmain;
+
+    if (warp == MMA_LOAD_WARP) {
+        // =============================================== loader =====================================================
+        // all 32 lanes issue bulk copies (one channel row each); lane 0 arms the transaction count first
+        uint32_t lit = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
+            const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;          // bytes per channel row (multiple of 16)
+            for (int kb = 0; kb < nkb; ++kb, ++lit) {
+                const int r = lit % q.ring;
+                if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
+                unsigned char* slot = s_raw + (size_t)r * slot_bytes;
+                const int rows = min(MMA_KB, q.K - kb * MMA_KB);
+                if (lane == 0) {
+                    uint32_t bytes = (uint32_t)rows * len * (has_aux ? 2 : 1);
+                    if (PRO == 2 && kb == 0) bytes += 6 * len;
+                    mbar_expect_tx(&raw_full[r], bytes);
+                }
+                __syncwarp();
+                if (lane < rows) {
+                    const int k = kb * MMA_KB + lane;
+                    bulk_g2s(slot + lane * (MMA_TP * 4), src_row(q, b, k) + p0, len, &raw_full[r]);
+                    if (has_aux) {
+                        const int ka = PRO == 2 ? k % gsize : k;
+                        bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0, len, &raw_full[r]);
+                    }
+                }
+                if (PRO == 2 && kb == 0 && lane < 6)
+                    bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
+            }
+        }
+    } else if (warp < MMA_EPI_WARP0) {
+        // =============================================== producers =================================================
+        const int pix = tid & (MMA_TP - 1), half = tid >> 7;
+        uint32_t it = 0;       // K-block counter (same sequence as the loader and the MMA warp)
+        // byte offsets of this thread's four 16-byte groups inside the swizzled operand panel
+        uint32_t soff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) soff[i] = sw128_off(pix, half + 2 * i);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
+            const bool pvalid = p0 + pix < HW;
+            float mu = 0.f, rs = 1.f;
+            float gmu0 = 0.f, gmu1 = 0.f, gmu2 = 0.f, grs0 = 1.f, grs1 = 1.f, grs2 = 1.f;
+            if (PRO == 1 || PRO == 3) {
+                // LayerNorm statistics over all K channels of this pixel, from the raw ring (all K blocks of the tile)
+                float s = 0.f;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1);
+                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                    const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const int k2 = 2 * kk + half;
+                        if (k2 < kmax) s += raw[k2 * MMA_TP];
+                    }
+                }
+                prod_sync();                       // the previous tile's readers of s_part are done
+                s_part[half * MMA_TP + pix] = s;
+                prod_sync();
+                mu = (s_part[pix] + s_part[MMA_TP + pix]) / (float)q.K;
+                float v = 0.f;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                    const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const int k2 = 2 * kk + half;
+                        if (k2 < kmax) { const float d = raw[k2 * MMA_TP] - mu; v += d * d; }
+                    }
+                }
+                prod_sync();
+                s_part[half * MMA_TP + pix] = v;
+                prod_sync();
+                rs = 1.0f / sqrtf((s_part[pix] + s_part[MMA_TP + pix]) / (float)q.K + 1e-5f);
+            }
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int r = it % q.ring;
+                const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
+                mbar_wait(&raw_full[r], (it / q.ring) & 1);
+                if (PRO == 2 && kb == 0) {
+                    const float* st = raw + 2 * (MMA_SLOT_BYTES / 4);
+                    gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
+                    gmu2 = st[4 * MMA_TP]; grs2 = st[5 * MMA_TP];
+                }
+                const int s = it % q.nstage;
+                unsigned char* stage = s_stage + s * stage_bytes;
+                const int kleft = q.K - kb * MMA_KB;                      // valid channels in this block (may exceed 32)
+                const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
+                const float* gam = s_gam + kb * MMA_KB;
+                const float* bet = s_bet + kb * MMA_KB;
+                if (it >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((it / q.nstage) - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = half + 2 * i;
+                    if (c < nchunks_used) {
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int kk = 4 * c + j;
+                            float x = raw[kk * MMA_TP];
+                            if (PRO == 1) {
+                                x = (x - mu) * rs * gam[kk] + bet[kk];
+                            } else if (PRO == 2) {
+                                const int g = (kb * MMA_KB + kk) / gsize;
+                                const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2);
+                                const float gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
+                                x = ((x - gm) * gr * gam[kk] + bet[kk]) * raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
+                            } else if (PRO == 3) {
+                                const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
+                                x = ((x - mu) * rs * gam[kk] + bet[kk]) * x1 + x1;
+                            }
+                            if (!pvalid || kk >= kleft) x = 0.f;
+                            hi[j] = to_tf32(x);
+                            lo[j] = to_tf32(x - hi[j]);
+                        }
+                        *reinterpret_cast<float4*>(stage + soff[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        if (PASSES == 3) *reinterpret_cast<float4*>(stage + a_bytes + soff[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                mbar_arrive(&raw_empty[r]);            // this thread is done with the raw slot
+                if (!q.b_resident) {
+                    const float4* src = reinterpret_cast<const float4*>(bsrc + (size_t)kb * 2 * q.Nc * 32);
+                    float4* dst = reinterpret_cast<float4*>(stage + 2 * a_bytes);
+                    for (int i = tid; i < panels * q.Nc * 8; i += MMA_PROD_THREADS) dst[i] = src[i];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&a_full[s]);
+            }
+        }
+    } else if (warp == MMA_MMA_WARP) {
+        // =============================================== MMA issuer ================================================
+        uint32_t it = 0, titer = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+            if (titer >= 1) mbar_wait(acc_empty, (titer - 1) & 1);        // the epilogue has drained the accumulators
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            bool corr_started = false;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % q.nstage;
+                mbar_wait(&a_full[s], (it / q.nstage) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_hi = smem_u32(s_stage + s * stage_bytes), a_lo = a_hi + a_bytes;
+                    const uint32_t b_hi = q.b_resident ? smem_u32(s_bres) + (uint32_t)kb * 2 * b_bytes : a_hi + 2 * a_bytes;
+                    const uint32_t b_lo = b_hi + b_bytes;
+                    const int ksteps = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 3;
+                    const uint32_t d_main = tmem_base + (uint32_t)((kb % nmain) * q.Nc);
+                    const uint32_t d_corr = tmem_base + (uint32_t)(nmain * q.Nc);
+                    for (int t = 0; t < ksteps; ++t) {
+                        const uint32_t koff = (uint32_t)t * 32;       // 8 tf32 = 32 bytes along K inside the swizzle atom
+                        umma_tf32(d_main, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc, (kb >= nmain || t > 0) ? 1u : 0u);
+                        if (PASSES == 3) {
+                            umma_tf32(d_corr, make_desc(a_hi + koff), make_desc(b_lo + koff), q.idesc, corr_started ? 1u : 0u);
+                            umma_tf32(d_corr, make_desc(a_lo + koff), make_desc(b_hi + koff), q.idesc, 1u);
+                            corr_started = true;
+                        }
+                    }
+                    umma_commit(&a_empty[s]);
+                    if (kb == nkb - 1) umma_commit(acc_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =============================================== epilogue ==================================================
+        // 8 warps: TMEM lane quadrant = warp % 4, the two warps of a quadrant split the 16-column groups
+        const int lane_grp = warp & 3, col_half = (warp - MMA_EPI_WARP0) >> 2;
+        const int row = lane_grp * 32 + lane;
+        const int nused = min(nmain, nkb);
+        const int ncol16 = q.Nc >> 4;
+        const int c16_mid = (ncol16 + 1) >> 1;
+        const int c16_begin = col_half == 0 ? 0 : c16_mid, c16_end = col_half == 0 ? c16_mid : ncol16;
+        const bool has_res = q.res != nullptr, has_film = q.film_mul != nullptr, has_bias = q.bias != nullptr;
+        const float res_coef = q.res_coef;
+        const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        uint32_t titer = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+            const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
+            const int pe = p0 + row;
+            const bool valid = pe < HW;
+            const size_t base = ((size_t)b * q.N + (size_t)chunk * q.Nc) * HW + (valid ? pe : 0);
+            // prefetch the residual of this warp's first 16 output channels while the MMAs of this tile are still running
+            float rpre[16];
+            if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nl = c16_begin * 16 + j;
+                    rpre[j] = (valid && c16_begin < c16_end && chunk * q.Nc + nl < q.N) ? q.res[base + (size_t)nl * HW] : 0.f;
+                }
+            }
+            mbar_wait(acc_full, titer & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c16 = c16_begin; c16 < c16_end; ++c16) {
+                float acc[16];
+                {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + (uint32_t)(c16 * 16), r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
+                }
+                for (int a = 1; a < nused; ++a) {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + (uint32_t)(a * q.Nc + c16 * 16), r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                }
+                if (PASSES == 3) {
+                    uint32_t r[16];
+                    tmem_ld16(tlane + (uint32_t)(nmain * q.Nc + c16 * 16), r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                }
+                if (c16 == c16_end - 1) {        // this warp's TMEM reads of the tile are complete: hand the accumulators back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(acc_empty);
+                }
+                const int n0 = chunk * q.Nc + c16 * 16;
+                if (valid) {
+                    float* op = q.out + base + (size_t)(c16 * 16) * HW;
+                    if (has_bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += (n0 + j < q.N) ? q.bias[n0 + j] : 0.f;
+                    }
+                    if (has_film) {
+                        const float* fm = q.film_mul + base + (size_t)(c16 * 16) * HW;
+                        const float* fa = q.film_add + base + (size_t)(c16 * 16) * HW;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < q.N) acc[j] = acc[j] * fm[(size_t)j * HW] + fa[(size_t)j * HW];
+                    }
+                    if (has_res) {
+                        if (c16 == c16_begin) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] += res_coef * rpre[j];
+                        } else {
+                            const float* rp = q.res + base + (size_t)(c16 * 16) * HW;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (n0 + j < q.N) acc[j] += res_coef * rp[(size_t)j * HW];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < q.N) op[(size_t)j * HW] = acc[j];
+                }
+            }
+            if (c16_begin >= c16_end) {          // a warp without columns (Nc == 16) still takes part in the hand-back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(acc_empty);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == MMA_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)q.tmem_cols) : "memory");
+    }
+}
+
+// per-pixel LayerNorm statistics of G channel groups: stats[b][g][0] = mean, stats[b][g][1] = 1/sqrt(var + eps)
+__global__ void __launch_bounds__(256) k_group_stats(const float* __restrict__ x, float* __restrict__ stats, int C, int HW, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*G*HW
+    if (i >= total) return;
+    const int p = (int)(i % HW);
+    const long long bg = i / HW;
+    const float* xp = x + (size_t)bg * C * HW + p;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += xp[(size_t)c * HW];
+    const float mu = s / (float)C;
+    float v = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float d = xp[(size_t)c * HW] - mu;
+        v += d * d;
+    }
+    stats[(size_t)bg * 2 * HW + p] = mu;
+    stats[((size_t)bg * 2 + 1) * HW + p] = 1.0f / sqrtf(v / (float)C + 1e-5f);
+}
+
+struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
+
+static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
+    const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
+    const size_t slot = (size_t)MMA_SLOT_BYTES * (prologue >= 2 ? 2 : 1) + (prologue == 2 ? 6 * MMA_TP * 4 : 0);
+    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 6) * sizeof(uint64_t) + 64;
+    const size_t budget = 227 * 1024;
+    const int ring_min = (prologue == 1 || prologue == 3) ? max(nkb, 2) : 2;  // LN needs all K blocks of a tile resident
+    PwMmaPlan best;
+    bool found = false;
+    for (int resident = 1; resident >= 0; --resident)
+        for (int nstage = 2; nstage >= 1; --nstage) {
+            const size_t fixed = misc + (resident ? (size_t)nkb * 2 * b_bytes : 0) + nstage * (2 * a_bytes + (resident ? 0 : 2 * b_bytes));
+            if (fixed + ring_min * slot > budget) continue;
+            int ring = (int)((budget - fixed) / slot);
+            if (ring > MMA_MAX_RING) ring = MMA_MAX_RING;
+            PwMmaPlan p{resident, nstage, ring, fixed + ring * slot};
+            // prefer: deep ring (>= 4 slots beyond the minimum is plenty), then residency, then two stages
+            const int score = min(ring - ring_min, 3) * 4 + resident * 2 + (nstage - 1);
+            const int best_score = found ? min(best.ring - ring_min, 3) * 4 + best.resident * 2 + (best.nstage - 1) : -1;
+            if (score > best_score) { best = p; found = true; }
+        }
+    if (found) *out = best;
+    return found;
+}
+#endif  // !FDN_EMU
+
+FDN_API int fdn_has_tcgen05() {
+#ifdef FDN_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+// stats[b][g][0][p] = mean over the C channels of group g, stats[b][g][1][p] = 1/sqrt(biased var + 1e-5); x [B][G*C][HW]
+FDN_API int fdn_group_stats(const float* x, float* stats, int B, int G, int C, int HW, cudaStream_t st) {
+#ifdef FDN_EMU
+    fdn_set_error("fdn_group_stats: not available in the host emulation build");
+    return -1;
+#else
+    FDN_REQUIRE(x && stats && B > 0 && G > 0 && C > 0 && HW > 0, "bad arguments");
+    long long total = (long long)B * G * HW;
+    k_group_stats<<<fdn_cdiv(total, 256), 256, 0, st>>>(x, stats, C, HW, total);
+    return fdn_check_launch("k_group_stats");
+#endif
+}
+
+// Tensor-core 1x1 convolution.  bpack is the host-packed weight (see fdn_tip2025_b200/packing.py): for every output chunk of
+// Nc (multiple of 16, <= 256) channels and every block of 32 input channels, a [Nc][32] tf32-hi panel followed by the tf32-lo
+// panel, both in the K-major SWIZZLE_128B image.  nchunks*Nc >= N.  prologue: 0 none, 1 LayerNorm over the K inputs,
+// 2 FDSA gate (three LayerNorm groups of K/3 channels with precomputed `stats`, times v_value = aux), 3 FCAFFN mix
+// LN(src)*aux + aux.  passes: 3 = 3xTF32 (fp32-level accuracy), 1 = single TF32.  HW must be a multiple of 4.
+FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, const float* bpack, int N, int Nc, int nchunks,
+                       int prologue, const float* ln_w, const float* ln_b, const float* aux, long long aux_bs, const float* stats,
+                       const float* bias, const float* film_mul, const float* film_add, const float* res, float res_coef,
+                       float* out, int B, int HW, int passes, cudaStream_t st) {
+#ifdef FDN_EMU
+    fdn_set_error("fdn_pw_mma: tcgen05 kernels are not available in the host emulation build");
+    return -1;
+#else
+    FDN_REQUIRE(src0 && bpack && out && B > 0 && HW > 0 && c0 > 0 && N > 0, "bad arguments");
+    FDN_REQUIRE(Nc % 16 == 0 && Nc >= 16 && Nc <= 256 && (long long)nchunks * Nc >= N, "bad output chunking");
+    FDN_REQUIRE(prologue >= 0 && prologue <= 3 && (passes == 1 || passes == 3), "bad mode");
+    FDN_REQUIRE((film_mul == nullptr) == (film_add == nullptr), "film needs both maps");
+    FDN_REQUIRE(HW % 4 == 0, "HW must be a multiple of 4 (16-byte bulk copies)");
+    if (prologue) FDN_REQUIRE(ln_w && ln_b && !src1, "LayerNorm prologue needs gamma/beta and a single source");
+    if (prologue >= 2) FDN_REQUIRE(aux != nullptr && fdn_aligned16(aux) && aux_bs % 4 == 0, "prologue needs a 16-byte aligned aux tensor");
+    if (prologue == 2) FDN_REQUIRE(c0 % 3 == 0 && stats && fdn_aligned16(stats), "FDSA gate needs 3 equal groups and their statistics");
+    FDN_REQUIRE(fdn_aligned16(bpack) && fdn_aligned16(src0) && (!src1 || fdn_aligned16(src1)), "pointers must be 16-byte aligned");
+    PwMmaParams q;
+    q.src0 = src0; q.src1 = src1; q.C0 = c0; q.C1 = src1 ? c1 : 0;
+    q.K = q.C0 + q.C1;
+    q.Kpad = (q.K + 7) & ~7;
+    q.N = N; q.Nc = Nc; q.HW = HW; q.B = B;
+    q.bpack = bpack; q.prologue = prologue; q.ln_w = ln_w; q.ln_b = ln_b; q.aux = aux; q.aux_bs = aux_bs; q.stats = stats;
+    q.bias = bias; q.film_mul = film_mul; q.film_add = film_add; q.res = res; q.res_coef = res_coef; q.out = out;
+    q.passes = passes;
+    // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+    q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
+    const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
+    PwMmaPlan plan;
+    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, &plan), "tile does not fit in shared memory");
+    q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
+    const int ncorr = passes == 3 ? 1 : 0;
+    q.nmain = 1;
+    if (nkb >= 2) q.nmain = min(min(3, nkb), (512 / Nc) - ncorr);
+    if (q.nmain < 1) q.nmain = 1;
+    q.tmem_cols = 32;
+    while (q.tmem_cols < (q.nmain + ncorr) * Nc) q.tmem_cols <<= 1;
+    FDN_REQUIRE(q.tmem_cols <= 512, "accumulators do not fit in tensor memory");
+    FDN_REQUIRE(nkb * MMA_KB <= MMA_MAX_K, "too many input channels");
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int ntiles = fdn_cdiv(HW, MMA_TP) * B;
+    const int gx = min(ntiles, max(1, num_sms / nchunks));
+    void (*kern)(PwMmaParams) = nullptr;
+    switch (prologue * 2 + (passes == 3 ? 1 : 0)) {
+        case 0: kern = k_pw_mma<0, 1>; break;
+        case 1: kern = k_pw_mma<0, 3>; break;
+        case 2: kern = k_pw_mma<1, 1>; break;
+        case 3: kern = k_pw_mma<1, 3>; break;
+        case 4: kern = k_pw_mma<2, 1>; break;
+        case 5: kern = k_pw_mma<2, 3>; break;
+        case 6: kern = k_pw_mma<3, 1>; break;
+        default: kern = k_pw_mma<3, 3>; break;
+    }
+    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    const int ki = prologue * 2 + (passes == 3 ? 1 : 0);
+    if (!configured[ki]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
+        configured[ki] = true;
+    }
+    kern<<<dim3(gx, nchunks, 1), dim3(MMA_THREADS), plan.smem, st>>>(q);
+    return fdn_check_launch("k_pw_mma");
+#endif
+}

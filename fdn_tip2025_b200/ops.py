@@ -103,6 +103,26 @@ def pw_conv(srcs, wt, out, bias=None, ln=None, act=0, film=None, res=None, res_c
               bs, ps, rs, b, n, h, w, _stream())
 
 
+def has_tcgen05():
+    return _lib.load().fdn_has_tcgen05() == 1
+
+
+def pw_mma(srcs, packed, out, prologue=0, ln=None, aux=None, aux_bs=0, stats=None, bias=None, film=None, res=None, res_coef=1.0, passes=3):
+    """srcs: one or two [B,C,H,W] tensors (channel concat); packed = packing.pack_weight(w) on the same device."""
+    bpack, n, nc, nchunks = packed
+    b, _, h, w = srcs[0].shape
+    s1 = srcs[1] if len(srcs) > 1 else None
+    _lib.call("fdn_pw_mma", _p(srcs[0]), srcs[0].shape[1], _p(s1), s1.shape[1] if s1 is not None else 0, _p(bpack), n, nc, nchunks,
+              prologue, _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, _p(aux), aux_bs, _p(stats), _p(bias),
+              _p(film[0]) if film else None, _p(film[1]) if film else None, _p(res), float(res_coef), _p(out), b, h * w, passes,
+              _stream())
+
+
+def group_stats(x, stats, groups):
+    b, gc, h, w = x.shape
+    _lib.call("fdn_group_stats", _p(x), _p(stats), b, groups, gc // groups, h * w, _stream())
+
+
 def chan_ln(x, out, gamma, beta, groups=1, mul=None, mul_bs=0, add=None, add_bs=0):
     b, gc, h, w = x.shape
     _lib.call("fdn_chan_ln", _p(x), _p(out), _p(gamma), _p(beta), _p(mul), mul_bs, _p(add), add_bs, b, groups, gc // groups,

@@ -1,0 +1,47 @@
+"""Host-side weight packing for the tcgen05 1x1-convolution kernel (csrc/pw_mma.cu).
+
+The B operand of tcgen05.mma is read from shared memory in the canonical K-major SWIZZLE_128B layout.  Packing the
+weight once (at load_state_dict / first forward) into that exact image lets the kernel fill its B stage with a linear,
+coalesced copy.  Layout: [chunk][k-block of 32][hi, lo][Nc rows][32 floats], where inside a row the 16-byte group g of
+row n is stored at group position g ^ (n % 8); hi = tf32(w), lo = tf32(w - hi) (the 3xTF32 split).
+"""
+import torch
+
+
+def tf32_round(x):
+    """cvt.rna.tf32.f32: round to 10 mantissa bits, ties away from zero."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def chunking(n):
+    """Output-channel chunking: nchunks chunks of Nc (multiple of 16, <= 256) columns of TMEM."""
+    nchunks = (n + 255) // 256
+    per = (n + nchunks - 1) // nchunks
+    nc = (per + 15) // 16 * 16
+    return nc, nchunks
+
+
+def pack_weight(w):
+    """w: [N, K] fp32 -> (bpack flat fp32 tensor, N, Nc, nchunks)."""
+    w = w.detach().float()
+    n, k = w.shape
+    nc, nchunks = chunking(n)
+    kpad = (k + 7) // 8 * 8
+    nkb = (kpad + 31) // 32
+    wp = torch.zeros(nchunks * nc, nkb * 32, dtype=torch.float32, device=w.device)
+    # chunk c holds output channels [c*nc, (c+1)*nc) of the *padded* numbering == real numbering (padding only at the end
+    # of each chunk would renumber channels, so pad at the very end and let every chunk but the last be full)
+    wp[:n, :k] = w
+    hi = tf32_round(wp)
+    lo = tf32_round(wp - hi)
+    rows = torch.arange(nc, device=w.device)
+    grp = torch.arange(8, device=w.device)
+    src_grp = grp[None, :] ^ (rows[:, None] & 7)            # stored position g holds source group g ^ (n%8)
+    out = []
+    for t in (hi, lo):
+        t = t.view(nchunks, nc, nkb, 8, 4).permute(0, 2, 1, 3, 4)          # [chunk][kb][n][group][4]
+        idx = src_grp[None, None, :, :, None].expand(nchunks, nkb, nc, 8, 4)
+        out.append(torch.gather(t, 3, idx))
+    packed = torch.stack(out, 2).contiguous()                # [chunk][kb][2][n][8][4]
+    return packed.view(-1), n, nc, nchunks

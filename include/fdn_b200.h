@@ -80,6 +80,21 @@ int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1, int c1
                 const float* film_mul, const float* film_add, const float* res, float res_coef, const float* img_scale,
                 float* out, long long out_bs, long long out_ps, int out_rs, int B, int N, int H, int W, cudaStream_t st);
 
+/* Tensor-core (tcgen05, kind::tf32, accumulator in TMEM) 1x1 convolution for the FDformer blocks: M = 128 pixels per CTA,
+ * N <= 256 output channels per chunk.  bpack is the weight packed by fdn_tip2025_b200/packing.py into the K-major
+ * SWIZZLE_128B shared-memory image (tf32 hi panel + tf32 lo panel per 32-channel block).  prologue (applied per pixel while
+ * the A operand is built): 0 none, 1 LayerNorm over the K inputs (FDN_arch.py:671,673), 2 FDSA gate = three LayerNorm groups
+ * (statistics from fdn_group_stats) times v_value=aux (FDN_arch.py:633-639), 3 FCAFFN mix LN(src)*aux + aux (FDN_arch.py:420).  Epilogue: +bias,
+ * *film_mul+film_add, +res_coef*res.  passes: 3 = 3xTF32 split (fp32-level accuracy), 1 = single TF32. */
+int fdn_has_tcgen05(void);
+int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, const float* bpack, int N, int Nc, int nchunks, int prologue,
+               const float* ln_w, const float* ln_b, const float* aux, long long aux_bs, const float* stats, const float* bias,
+               const float* film_mul, const float* film_add, const float* res, float res_coef, float* out, int B, int HW, int passes,
+               cudaStream_t st);
+/* Per-pixel LayerNorm statistics of G channel groups of x [B][G*C][HW]: stats [B][G][2][HW] = (mean, 1/sqrt(var + 1e-5)).
+ * Feeds prologue 2 of fdn_pw_mma (FDSA norm1..3, FDN_arch.py:633-635). */
+int fdn_group_stats(const float* x, float* stats, int B, int G, int C, int HW, cudaStream_t st);
+
 /* Grouped channel LayerNorm (FDN_arch.py:326-342, 420, 633-638):
  * out[b][g*C+c][p] = LN_g(in[b][g*C+c][p]) * mul[b*mul_bs + c*HW + p] + add[b*add_bs + c*HW + p]; mul/add may be NULL. */
 int fdn_chan_ln(const float* in, float* out, const float* gamma, const float* beta, const float* mul, long long mul_bs,

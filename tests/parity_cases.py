@@ -303,3 +303,56 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7):
         for g, r in zip(got[1:], ref[1:]):
             assert (g.double().cpu() - r).abs().max().item() <= 1e-3
     return mx, ps
+
+
+# ----------------------------------------------------------------------------------------- tcgen05 1x1 convolution
+def case_pw_mma(dev, k, n, hw=(16, 24), prologue=0, passes=3, two_src=False, seed=0, tol=(2e-6, 8e-6)):
+    from fdn_tip2025_b200 import packing
+    b, (h, w) = 2, hw
+    x = rnd(b, k, h, w, seed=seed + 1)
+    wgt = rnd(n, k, seed=seed + 2) / (k ** 0.5)
+    bias, res = rnd(n, seed=seed + 3), rnd(b, n, h, w, seed=seed + 4)
+    fm, fa = rnd(b, n, h, w, seed=seed + 5), rnd(b, n, h, w, seed=seed + 6)
+    xf, wf = x.float().double(), wgt.float().double()
+    packed = packing.pack_weight(dev32(wgt, dev))
+    out = torch.empty(b, n, h, w, device=dev)
+    kw = dict(bias=dev32(bias, dev), res=dev32(res, dev), res_coef=1.0, passes=passes)
+
+    def ln(t, g, bt):
+        mu = t.mean(1, keepdim=True)
+        var = ((t - mu) ** 2).mean(1, keepdim=True)
+        return (t - mu) / torch.sqrt(var + 1e-5) * g.view(1, -1, 1, 1) + bt.view(1, -1, 1, 1)
+
+    if prologue == 0:
+        srcs = [dev32(x, dev)]
+        a = xf
+        if two_src:
+            k1 = k // 3
+            srcs = [dev32(x[:, :k1], dev), dev32(x[:, k1:], dev)]
+        ops.pw_mma(srcs, packed, out, film=(dev32(fm, dev), dev32(fa, dev)), **kw)
+        ref = (F.conv2d(a, wf[:, :, None, None], bias.float().double()) * fm.float().double() + fa.float().double()) + res.float().double()
+    elif prologue == 1:
+        g, bt = rnd(k, seed=seed + 7) + 1.5, rnd(k, seed=seed + 8)
+        ops.pw_mma([dev32(x, dev)], packed, out, prologue=1, ln=(dev32(g, dev), dev32(bt, dev)), **kw)
+        ref = F.conv2d(ln(xf, g.float().double(), bt.float().double()), wf[:, :, None, None], bias.float().double()) + res.float().double()
+    elif prologue == 2:
+        e = k // 3
+        g, bt = rnd(3, e, seed=seed + 7) + 1.5, rnd(3, e, seed=seed + 8)
+        hid = rnd(b, 4 * e, h, w, seed=seed + 9)
+        hd = dev32(hid, dev)
+        xd = dev32(x, dev)
+        stats = torch.empty(b, 3, 2, h * w, device=dev)
+        ops.group_stats(xd, stats, 3)
+        ops.pw_mma([xd], packed, out, prologue=2, ln=(dev32(g, dev), dev32(bt, dev)), aux=hd.view(-1)[3 * e * h * w:],
+                   aux_bs=4 * e * h * w, stats=stats, **kw)
+        vv = hid[:, 3 * e:].float().double()
+        a = torch.cat([ln(xf[:, i * e:(i + 1) * e], g[i].float().double(), bt[i].float().double()) * vv for i in range(3)], 1)
+        ref = F.conv2d(a, wf[:, :, None, None], bias.float().double()) + res.float().double()
+    else:
+        g, bt = rnd(k, seed=seed + 7) + 1.5, rnd(k, seed=seed + 8)
+        x1 = rnd(b, k, h, w, seed=seed + 9)
+        ops.pw_mma([dev32(x, dev)], packed, out, prologue=3, ln=(dev32(g, dev), dev32(bt, dev)), aux=dev32(x1, dev), aux_bs=k * h * w, **kw)
+        a = ln(xf, g.float().double(), bt.float().double()) * x1.float().double() + x1.float().double()
+        ref = F.conv2d(a, wf[:, :, None, None], bias.float().double()) + res.float().double()
+    sync(dev)
+    return compare("pw_mma K=%d N=%d pro=%d passes=%d" % (k, n, prologue, passes), out, ref, rel_l2=tol[0], max_rel=tol[1])
