@@ -143,7 +143,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from fdn_tip2025_b200 import _lib, archs, synth
+    from fdn_tip2025_b200 import _lib, archs, sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,7 +165,7 @@ def main():
     lp = lp.to(dev).eval()
 
     # image i of the global batch goes to rank i mod world (reference validation rule, image_restoration_model.py:731)
-    idx = [rank + world * j for j in range(B)]
+    idx = sharding.shard_indices(rank, world, B)
     host = torch.cat([synth.low_light_images(1, H, W, first_index=i) for i in idx], 0).pin_memory()
     x = host.to(dev, non_blocking=True)
     ratio = lp(x)                                   # LPNet is outside the timed region: the metric is the FDN forward
@@ -185,9 +185,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = sharding.max_over_ranks(torch.tensor([ms], device=dev))
         barrier()
         return t.item()
 

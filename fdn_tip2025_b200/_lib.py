@@ -23,6 +23,7 @@ SIGNATURES = {
     "fdn_spec_mlp": "plliips",
     "fdn_fdffn_patch": "ppppiiiis",
     "fdn_fdsa_patch": "pppiiiis",
+    "fdn_fdsa_patch_dw": "pppppiiiis",
     "fdn_pw_conv": "piipiipiippppipppfpplliiiiis",
     "fdn_has_tcgen05": "",
     "fdn_pw_mma": "pipipiiiippplpppppfpiiis",

@@ -230,22 +230,20 @@ def _fdsa(cx, x, p):
     e = schema.expand_dim(c)
     hid = _new(x, b, 4 * e, h, w)
     _conv1x1(cx, [x], p + "attn.to_hidden.weight", hid, ln=cx.ln(p + "norm1."))
-    hid_dw = _new(x, b, 4 * e, h, w)
-    ops.dwconv3(hid, cx.flat(p + "attn.to_hidden_dw.weight"), hid_dw, mode=0)
+    o, vv = _new(x, b, 3 * e, h, w), _new(x, b, e, h, w)
+    # depthwise 3x3, 8x8 rFFT, bin algebra and inverse FFT in one kernel; vv = convolved v_value group
+    ops.fdsa_patch_dw(hid, cx.flat(p + "attn.to_hidden_dw.weight"), cx.flat(p + "attn.fft"), o, vv)
     del hid
-    o = _new(x, b, 3 * e, h, w)
-    ops.fdsa_patch(hid_dw, cx.flat(p + "attn.fft"), o)
     g3, b3 = cx.ln3(p + "attn.")
-    vv = hid_dw.view(-1)[3 * e * h * w:]                     # v_value group, batch stride 4E*HW
     out = _new(x, b, c, h, w)
     mode = _gemm_mode()
     if mode == "ffma":
-        ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=4 * e * h * w)
+        ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=e * h * w)
         ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
     else:   # norm1..3, the v_value gate and project_out in one kernel (LayerNorm statistics from a small pre-pass)
         stats = _new(x, b, 3, 2, h * w)
         ops.group_stats(o, stats, 3)
-        ops.pw_mma([o], cx.packed(p + "attn.project_out.weight"), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=4 * e * h * w,
+        ops.pw_mma([o], cx.packed(p + "attn.project_out.weight"), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=e * h * w,
                    stats=stats, res=x, res_coef=1.0, passes=1 if mode == "tf32" else 3)
     return out
 

@@ -220,71 +220,86 @@ FDN_API int fdn_convt4s2(const float* in, const float* w, const float* bias, flo
 //   mode 0: out[c] = conv(in[c]; w[c])            mode 1: out[c] = gelu(conv(in[c]; w[c]))
 //   mode 2: gate, w is [2C][9]: out[j] = gelu(conv(in[j/2]; w[j])) * conv(in[(C+j)/2]; w[C+j])
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dw_rows(const float* __restrict__ plane, int H, int W, int y, int x0, float r[3][6]) {
+// Each thread produces a 4 (x) by 4 (y) block of one output channel: six input rows of six values (one aligned float4 plus
+// the two neighbours) feed sixteen outputs, i.e. 18 load instructions per 16 outputs.
+__device__ __forceinline__ void dw_load6(const float* __restrict__ plane, int H, int W, int y0, int x0, float r[6][6]) {
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        int yy = y + dy - 1;
-        bool rowok = yy >= 0 && yy < H;
-        const float* p = plane + (size_t)(rowok ? yy : 0) * W;
+    for (int dy = 0; dy < 6; ++dy) {
+        const int yy = y0 + dy - 1;
+        if (yy >= 0 && yy < H) {
+            const float* p = plane + (size_t)yy * W + x0;
+            const float4 m = *reinterpret_cast<const float4*>(p);
+            r[dy][0] = x0 > 0 ? p[-1] : 0.f;
+            r[dy][1] = m.x; r[dy][2] = m.y; r[dy][3] = m.z; r[dy][4] = m.w;
+            r[dy][5] = x0 + 4 < W ? p[4] : 0.f;
+        } else {
 #pragma unroll
-        for (int dx = 0; dx < 6; ++dx) {
-            int xx = x0 + dx - 1;
-            r[dy][dx] = (rowok && xx >= 0 && xx < W) ? p[xx] : 0.f;
+            for (int dx = 0; dx < 6; ++dx) r[dy][dx] = 0.f;
         }
     }
 }
-__device__ __forceinline__ void dw_apply(const float r[3][6], const float* __restrict__ w, float o[4]) {
+__device__ __forceinline__ void dw_apply16(const float r[6][6], const float* __restrict__ w, float o[4][4]) {
     float k[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) k[i] = w[i];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a = 0.f;
+    for (int y = 0; y < 4; ++y)
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int x = 0; x < 4; ++x) {
+            float a = 0.f;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * r[dy][j + dx];
-        o[j] = a;
-    }
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * r[y + dy][x + dx];
+            o[y][x] = a;
+        }
 }
 
 __global__ void __launch_bounds__(256) k_dwconv3(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                                                  int C, int H, int W, int mode, long long total) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*H*(W/4)
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*ceil(H/4)*(W/4)
     if (i >= total) return;
-    int W4 = W >> 2;
-    int x0 = (int)(i % W4) * 4;
+    const int W4 = W >> 2, H4 = (H + 3) >> 2;
+    const int x0 = (int)(i % W4) * 4;
     long long t = i / W4;
-    int y = (int)(t % H);
-    t /= H;
-    int c = (int)(t % C);
-    long long b = t / C;
-    float r[3][6], o[4];
+    const int y0 = (int)(t % H4) * 4;
+    t /= H4;
+    const int c = (int)(t % C);
+    const long long b = t / C;
+    float r[6][6], o[4][4];
     if (mode != 2) {
-        dw_rows(in + ((size_t)b * C + c) * H * W, H, W, y, x0, r);
-        dw_apply(r, w + c * 9, o);
+        dw_load6(in + ((size_t)b * C + c) * H * W, H, W, y0, x0, r);
+        dw_apply16(r, w + c * 9, o);
         if (mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fdn_gelu(o[j]);
+            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) o[y][x] = fdn_gelu(o[y][x]);
         }
     } else {
-        float o2[4];
-        int ca = c >> 1, cb = (C + c) >> 1;
-        dw_rows(in + ((size_t)b * C + ca) * H * W, H, W, y, x0, r);
-        dw_apply(r, w + c * 9, o);
-        if (cb != ca) dw_rows(in + ((size_t)b * C + cb) * H * W, H, W, y, x0, r);
-        dw_apply(r, w + (C + c) * 9, o2);
+        float o2[4][4];
+        const int ca = c >> 1, cb = (C + c) >> 1;
+        dw_load6(in + ((size_t)b * C + ca) * H * W, H, W, y0, x0, r);
+        dw_apply16(r, w + c * 9, o);
+        if (cb != ca) dw_load6(in + ((size_t)b * C + cb) * H * W, H, W, y0, x0, r);
+        dw_apply16(r, w + (C + c) * 9, o2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fdn_gelu(o[j]) * o2[j];
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) o[y][x] = fdn_gelu(o[y][x]) * o2[y][x];
     }
-    *reinterpret_cast<float4*>(out + (((size_t)b * C + c) * H + y) * W + x0) = make_float4(o[0], o[1], o[2], o[3]);
+    float* op = out + (((size_t)b * C + c) * H + y0) * W + x0;
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+        if (y0 + y < H) *reinterpret_cast<float4*>(op + (size_t)y * W) = make_float4(o[y][0], o[y][1], o[y][2], o[y][3]);
 }
 
 FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int C, int H, int W, int mode, cudaStream_t st) {
     FDN_REQUIRE(in && w && out && B > 0 && C > 0 && H > 0 && W > 0, "bad arguments");
     FDN_REQUIRE(W % 4 == 0 && fdn_aligned16(out), "W must be a multiple of 4 and out 16-byte aligned");
     FDN_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
-    long long total = (long long)B * C * H * (W / 4);
+    FDN_REQUIRE(fdn_aligned16(in), "in must be 16-byte aligned");
+    long long total = (long long)B * C * ((H + 3) / 4) * (W / 4);
     FDN_LAUNCH_SEQ(k_dwconv3, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, in, w, out, C, H, W, mode, total);
     return fdn_check_launch("k_dwconv3");
 }

@@ -125,6 +125,111 @@ __global__ void __launch_bounds__(128) k_fdsa_patch(const float* __restrict__ hi
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FDSA with the depthwise 3x3 (to_hidden_dw, FDN_arch.py:563,578) fused in front: four lanes per (channel, patch) -
+// q, k, v and v_value.  Every lane convolves its 10x10 halo window of the pre-dw hidden tensor in registers; the q/k/v
+// lanes then run the spectral algebra exactly as above, the v_value lane stores its convolved patch for the gate.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row10(const float* __restrict__ plane, int H, int W, int yy, int x0, float r[10]) {
+    if (yy >= 0 && yy < H) {
+        const float* p = plane + (size_t)yy * W + x0;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        r[0] = x0 > 0 ? p[-1] : 0.f;
+        r[1] = a.x; r[2] = a.y; r[3] = a.z; r[4] = a.w; r[5] = b.x; r[6] = b.y; r[7] = b.z; r[8] = b.w;
+        r[9] = x0 + 8 < W ? p[8] : 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) r[i] = 0.f;
+    }
+}
+
+// p[8*y + x] = sum_{dy,dx} k[dy][dx] * in[y0 + y + dy - 1][x0 + x + dx - 1], zero outside the image
+__device__ __forceinline__ void dw3_patch(const float* __restrict__ plane, const float* __restrict__ w, int H, int W, int y0, int x0,
+                                          float p[64]) {
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = w[i];
+    float r0[10], r1[10], r2[10];
+    load_row10(plane, H, W, y0 - 1, x0, r0);
+    load_row10(plane, H, W, y0, x0, r1);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        load_row10(plane, H, W, y0 + y + 1, x0, r2);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            float a = k[0] * r0[x];
+            a += k[1] * r0[x + 1]; a += k[2] * r0[x + 2];
+            a += k[3] * r1[x]; a += k[4] * r1[x + 1]; a += k[5] * r1[x + 2];
+            a += k[6] * r2[x]; a += k[7] * r2[x + 1]; a += k[8] * r2[x + 2];
+            p[8 * y + x] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { r0[i] = r1[i]; r1[i] = r2[i]; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_fdsa_patch_dw(const float* __restrict__ hid, const float* __restrict__ wdw,
+                                                       const float* __restrict__ wfft, float* __restrict__ out, float* __restrict__ vv,
+                                                       int E, int H, int W, long long nitems) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int t = lane >> 2, role = lane & 3;
+    const long long item = warp * 8 + t;
+    const bool valid = item < nitems;
+    const int pw = W >> 3, ph = H >> 3;
+    float p[64];
+    float2 S[8][5];
+    size_t off_out = 0;
+    int e = 0;
+    if (valid) {
+        int px = (int)(item % pw);
+        long long r = item / pw;
+        int py = (int)(r % ph);
+        r /= ph;
+        e = (int)(r % E);
+        long long b = r / E;
+        const int ch = role * E + e;
+        dw3_patch(hid + ((size_t)b * 4 * E + ch) * H * W, wdw + ch * 9, H, W, py * 8, px * 8, p);
+        const size_t sp = (size_t)(py * 8) * W + px * 8;
+        if (role == 3) {
+            store_patch(vv + ((size_t)b * E + e) * H * W + sp, W, p);
+        } else {
+            off_out = ((size_t)b * 3 * E + role * E + e) * H * W + sp;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) p[i] = 0.f;
+    }
+    rfft2_8x8(p, S);
+    const int l0 = 4 * t;
+#pragma unroll
+    for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            float wsel = (valid && role == 2) ? wfft[e * 40 + ky * 5 + kx] : 1.0f;
+            float sx = S[ky][kx].x * wsel, sy = S[ky][kx].y * wsel;
+            float2 q = make_float2(__shfl_sync(0xffffffffu, sx, l0), __shfl_sync(0xffffffffu, sy, l0));
+            float2 k = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 1), __shfl_sync(0xffffffffu, sy, l0 + 1));
+            float2 v = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 2), __shfl_sync(0xffffffffu, sy, l0 + 2));
+            float2 qk = cmul(q, k);
+            qk.x = fdn_rd(qk.x);
+            qk.y = fdn_rd(qk.y);
+            float A = sqrtf(qk.x * qk.x + qk.y * qk.y);
+            float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
+            float iq = 1.0f / sqrtf(qc.x * qc.x + qc.y * qc.y), ik = 1.0f / sqrtf(kc.x * kc.x + kc.y * kc.y);
+            float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));
+            float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));
+            float m = sqrtf(vc.x * vc.x + vc.y * vc.y);
+            float2 o;
+            if (role == 0) o = make_float2(m * u.x, m * u.y);
+            else if (role == 1) { float s = A / m; o = make_float2(s * vc.x, s * vc.y); }
+            else o = make_float2(A * u.x, A * u.y);
+            S[ky][kx] = o;
+        }
+    irfft2_8x8(S, p);
+    if (valid && role != 3) store_patch(out + off_out, W, p);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 // out = irfft2_8x8( rd(rfft2_8x8(x)) * wspec[c] ) + add.   x, add, out: [B][C][H][W]; wspec: [C][8][5] complex.
@@ -149,4 +254,17 @@ FDN_API int fdn_fdsa_patch(const float* hid, const float* wfft, float* out, int 
     long long warps = (n + 9) / 10;
     FDN_LAUNCH(k_fdsa_patch, dim3(fdn_cdiv(warps, 4)), dim3(128), 0, st, hid, wfft, out, E, H, W, n);
     return fdn_check_launch("k_fdsa_patch");
+}
+
+// FDSA bin algebra with to_hidden_dw fused: hid [B][4E][H][W] is the *pre*-depthwise hidden tensor, wdw [4E][9] the
+// depthwise weights.  out [B][3E][H][W] = (out1,out2,out3) before norm1..3, vv [B][E][H][W] = depthwise-convolved v_value.
+FDN_API int fdn_fdsa_patch_dw(const float* hid, const float* wdw, const float* wfft, float* out, float* vv, int B, int E, int H, int W,
+                              cudaStream_t st) {
+    FDN_REQUIRE(hid && wdw && wfft && out && vv && B > 0 && E > 0, "bad arguments");
+    FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
+    FDN_REQUIRE(fdn_aligned16(hid) && fdn_aligned16(out) && fdn_aligned16(vv), "pointers must be 16-byte aligned");
+    long long n = (long long)B * E * (H / 8) * (W / 8);
+    long long warps = (n + 7) / 8;
+    FDN_LAUNCH(k_fdsa_patch_dw, dim3(fdn_cdiv(warps, 4)), dim3(128), 0, st, hid, wdw, wfft, out, vv, E, H, W, n);
+    return fdn_check_launch("k_fdsa_patch_dw");
 }

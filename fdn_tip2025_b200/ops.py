@@ -80,6 +80,11 @@ def fdsa_patch(hid, wfft, out):
     _lib.call("fdn_fdsa_patch", _p(hid), _p(wfft), _p(out), b, c4 // 4, h, w, _stream())
 
 
+def fdsa_patch_dw(hid, wdw, wfft, out, vv):
+    b, c4, h, w = hid.shape
+    _lib.call("fdn_fdsa_patch_dw", _p(hid), _p(wdw), _p(wfft), _p(out), _p(vv), b, c4 // 4, h, w, _stream())
+
+
 # ------------------------------------------------------------------------------------------------ per pixel
 def pw_conv(srcs, wt, out, bias=None, ln=None, act=0, film=None, res=None, res_coef=1.0, img_scale=None, out_view=None):
     """srcs: list of (tensor [B,C,Hs,Ws], shift).  wt [K][N].  out [B,N,H,W] (or out_view=(bs, ps, rs) strides into `out`)."""

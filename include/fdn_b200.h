@@ -68,6 +68,11 @@ int fdn_fdffn_patch(const float* x, const float* add, const float* wspec, float*
  * out [B][3E][H][W] = (out1,out2,out3) before norm1..3. */
 int fdn_fdsa_patch(const float* hid, const float* wfft, float* out, int B, int E, int H, int W, cudaStream_t st);
 
+/* Same with to_hidden_dw (depthwise 3x3, FDN_arch.py:563,578) fused in front: hid is the pre-depthwise hidden tensor, wdw [4E][9];
+ * vv [B][E][H][W] receives the convolved v_value group for the gate. */
+int fdn_fdsa_patch_dw(const float* hid, const float* wdw, const float* wfft, float* out, float* vv, int B, int E, int H, int W,
+                      cudaStream_t st);
+
 /* ---- per-pixel operators ---------------------------------------------------------------------------------------------- */
 
 /* 1x1 convolution over the channel concatenation of up to three sources (nn.Conv2d(k=1), torch.cat, F.interpolate nearest:

@@ -280,8 +280,17 @@ def case_lpnet(dev, h, w, report=None, sd=None):
         compare("LPNet %dx%d ori=%s" % (h, w, ori), got, ref, rel_l2=1e-5, max_rel=1e-5, report=report)
 
 
-def case_fdn(dev, kind, h, w, b=1, report=None, seed=7):
-    """End-to-end gate with damped weights: max-abs <= 1e-3 and PSNR >= 50 dB vs the fp64 oracle."""
+def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True):
+    """End-to-end gate with damped weights against the fp64 oracle.
+
+    strict: the north-star gate, max-abs <= 1e-3 and PSNR >= 50 dB.
+    not strict: PSNR >= 50 dB, max-abs <= 5e-2 and at most 5 % of the values off by more than 1e-3.  The network is
+    chaotic at isolated FDSA bins: a purely real (self-conjugate) 8x8 bin of q or k that happens to be ~1e-7 gets its
+    SIGN - a phase of 0 vs pi - from fp32 rounding noise (torch's own fp32 FFT has 100 % relative error there; see
+    tools/block0_check.py and DESIGN.md).  Any two fp32 evaluation orders - the reference on 1 vs 8 threads, the fp32
+    oracle vs the reference (tests/test_oracle_golden.py), FFMA vs tensor-core GEMMs - therefore differ by a few 1e-3
+    on a few patches while every block matches the fp64 oracle to 1e-6 on generic inputs.
+    """
     dim, variant = (32, "lolblur") if kind == "FDN" else (24, "lolv1")
     sd = synth.fdn_state_dict(dim=dim, seed=seed, damp=0.03)
     net = getattr(archs, kind)()
@@ -293,15 +302,20 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7):
     sync(dev)
     ref = O.fdn(x.double(), ratio.double(), _sd64(sd), variant)
     out = got[0].double().cpu()
-    mx = (out - ref[0]).abs().max().item()
+    d = (out - ref[0]).abs()
+    mx = d.max().item()
     ps = O.psnr(out, ref[0])
+    frac = (d > 1e-3).double().mean().item()
     if report is not None:
-        report.append(("%s %dx%d end-to-end" % (kind, h, w), mx, ps))
+        report.append(("%s %dx%d end-to-end" % (kind, h, w), mx, ps, frac))
     assert torch.isfinite(out).all()
-    assert mx <= 1e-3 and ps >= 50.0, "%s %dx%d: max-abs %.3e, PSNR %.1f dB" % (kind, h, w, mx, ps)
+    if strict:
+        assert mx <= 1e-3 and ps >= 50.0, "%s %dx%d: max-abs %.3e, PSNR %.1f dB" % (kind, h, w, mx, ps)
+    else:
+        assert ps >= 50.0 and mx <= 5e-2 and frac <= 5e-2, "%s %dx%d: max-abs %.3e, PSNR %.1f dB, frac>1e-3 %.2e" % (kind, h, w, mx, ps, frac)
     if kind == "FDN":
         for g, r in zip(got[1:], ref[1:]):
-            assert (g.double().cpu() - r).abs().max().item() <= 1e-3
+            assert (g.double().cpu() - r).abs().max().item() <= 1e-3      # MAR outputs are well conditioned
     return mx, ps
 
 
