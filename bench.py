@@ -251,8 +251,16 @@ def main():
                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])}
         top = max(fam.items(), key=lambda kv: kv[1][0])
         ach = top[1][2] / (top[1][0] * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        tr_path = os.path.join(ROOT, "profiles", "r1_traffic_ratio.json")
+        if os.path.exists(tr_path):
+            with open(tr_path) as f:
+                tr = json.load(f)
+            if top[0] in tr:        # DRAM bytes / algorithmic bytes measured with ncu --set full for this kernel family
+                traffic = tr[top[0]]["ratio"] * top[1][2] / top[1][1]
+                traffic_src = "profiles/r1_traffic_ratio.json: ncu dram bytes / algorithmic bytes = %.2f" % tr[top[0]]["ratio"]
         roofline = {"kernel": top[0], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "share_of_step": top[1][0] / tot,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "share_of_step": top[1][0] / tot,
                     "bytes_per_launch": top[1][2] / top[1][1], "avg_launch_ms": top[1][0] / top[1][1]}
 
     fwd_alg = B_ALG_PER_PIXEL * H * W * (value) / 1e9 / world       # GB/s per GPU if the forward were ideally fused
@@ -269,7 +277,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FDN (LOL-Blur, dim 32) forward, %dx%d, %d images per GPU per step (BASELINE config 3: batch 64 "
                                    "sharded by image)" % (W, H, B),
-                       "weights": "synthetic, seed 0, net_p project_out x0.03", "precision": "fp32 FFMA everywhere",
+                       "weights": "synthetic, seed 0, net_p project_out x0.03", "precision": "fp32 I/O; 1x1 convs on tcgen05 in 3xTF32 (FDN_B200_GEMM=%s), everything else fp32 FFMA" % os.environ.get("FDN_B200_GEMM", "tf32x3"),
                        "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "micro_batch": archs._micro_batch(B, H, W), "ratio_i": "I_predict_net output, computed outside the timed region"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
