@@ -229,30 +229,43 @@ __device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// rows: real -> half spectrum
+// rows: real -> half spectrum, W even.  The W real samples of a row are packed into M = W/2 complex numbers
+// z[n] = x[2n] + i x[2n+1]; one length-M complex FFT gives Z, and
+//   X[k] = E[k] + w^k O[k],  E[k] = (Z[k] + conj Z[M-k]) / 2,  O[k] = -i (Z[k] - conj Z[M-k]) / 2,  w = e^{-2 pi i / W}
+// for k = 0..M (Z[M] = Z[0]).  Half the butterflies, shared memory and barriers of a length-W complex transform.
 // ---------------------------------------------------------------------------------------------------
-// in: nrows rows of W floats, row r at in + r*W.  out: row r at out + r*Wf, Wf = W/2+1.
-__global__ void __launch_bounds__(256) k_rows_r2c(const float* __restrict__ in, float2* __restrict__ out, FftPlanDev P,
-                                                  int nrows, int rows_per_cta) {
+// in: nrows rows of W floats, row r at in + r*W.  out: row r at out + r*Wf, Wf = W/2+1.  PM = plan of length M, twW = table of W.
+__global__ void __launch_bounds__(256) k_rows_r2c(const float* __restrict__ in, float2* __restrict__ out, FftPlanDev PM,
+                                                  const float2* __restrict__ twW, int nrows, int rows_per_cta) {
     FDN_DYN_SMEM(smem);
-    const int W = P.N, Wf = W / 2 + 1;
+    const int M = PM.N, Wf = M + 1;
     float2* a = reinterpret_cast<float2*>(smem);
-    float2* b = a + rows_per_cta * W;
+    float2* b = a + rows_per_cta * M;
     const int row0 = blockIdx.x * rows_per_cta;
     const int S = min(rows_per_cta, nrows - row0);
-    for (int i = threadIdx.x; i < S * W; i += blockDim.x) a[i] = make_float2(in[(size_t)row0 * W + i], 0.f);
+    const float2* src = reinterpret_cast<const float2*>(in + (size_t)row0 * 2 * M);      // rows are 8-byte aligned (W even)
+    for (int i = threadIdx.x; i < S * M; i += blockDim.x) a[i] = src[i];
     __syncthreads();
-    float2* res = fft_smem<-1>(P, a, b, S, W, 1);
+    float2* res = fft_smem<-1>(PM, a, b, S, M, 1);
     for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
-        int r = i / Wf, k = i - r * Wf;
-        float2 v = res[r * W + k];
-        if (k == 0 || 2 * k == W) v.y = 0.f;     // exact for real input
+        const int r = i / Wf, k = i - r * Wf;
+        const float2 zk = res[r * M + (k == M ? 0 : k)];
+        const float2 zc = res[r * M + (k == 0 ? 0 : M - k)];            // conj applied below
+        const float ex = 0.5f * (zk.x + zc.x), ey = 0.5f * (zk.y - zc.y);
+        const float dx = zk.x - zc.x, dy = zk.y + zc.y;                   // D = Z[k] - conj Z[M-k]
+        const float ox = 0.5f * dy, oy = -0.5f * dx;                      // O = -i D / 2
+        const float2 w = twW[k];
+        float2 v = make_float2(ex + (w.x * ox - w.y * oy), ey + (w.x * oy + w.y * ox));
+        if (k == 0 || k == M) v.y = 0.f;                                  // exact for real input
         out[(size_t)(row0 + r) * Wf + k] = v;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// rows: half spectrum -> real, with epilogue  out = img_scale[b] * (irfft * norm + res_coef * res)
+// rows: half spectrum -> real (inverse of the packing above), epilogue  out = img_scale[b] * (irfft * norm + res_coef * res)
+//   Z[k] = E[k] + i O[k],  E[k] = (X[k] + conj X[M-k]) / 2,  O[k] = conj(w^k) (X[k] - conj X[M-k]) / 2,  k = 0..M-1
+//   z = IDFT_M(Z) = M (x[2n] + i x[2n+1])
+// The imaginary parts of X[0] and X[M] are ignored, as torch.fft.irfft does.
 // ---------------------------------------------------------------------------------------------------
 struct RowsC2RParams {
     const float2* in;     // [nrows][Wf]
@@ -266,33 +279,41 @@ struct RowsC2RParams {
     int rows_per_image;   // C*H, to find b for img_scale
 };
 
-__global__ void __launch_bounds__(256) k_rows_c2r(RowsC2RParams q, FftPlanDev P) {
+__global__ void __launch_bounds__(256) k_rows_c2r(RowsC2RParams q, FftPlanDev PM, const float2* __restrict__ twW) {
     FDN_DYN_SMEM(smem);
-    const int W = P.N, Wf = W / 2 + 1;
+    const int M = PM.N, Wf = M + 1;
     float2* a = reinterpret_cast<float2*>(smem);
-    float2* b = a + q.rows_per_cta * W;
+    float2* b = a + q.rows_per_cta * (M + 1);
     const int row0 = blockIdx.x * q.rows_per_cta;
     const int S = min(q.rows_per_cta, q.nrows - row0);
+    // stage the half spectrum (M+1 bins per row) in b, then build Z in a
     for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
-        int r = i / Wf, k = i - r * Wf;
+        const int r = i / Wf, k = i - r * Wf;
         float2 v = q.in[(size_t)(row0 + r) * Wf + k];
-        if (k == 0 || 2 * k == W) {
-            v.y = 0.f;                       // C2R ignores the imaginary part of the DC / Nyquist bins
-            a[r * W + k] = v;
-        } else {
-            a[r * W + k] = v;
-            a[r * W + (W - k)] = make_float2(v.x, -v.y);
-        }
+        if (k == 0 || k == M) v.y = 0.f;
+        b[r * (M + 1) + k] = v;
     }
     __syncthreads();
-    float2* res = fft_smem<1>(P, a, b, S, W, 1);
-    for (int i = threadIdx.x; i < S * W; i += blockDim.x) {
-        int r = i / W;
-        size_t g = (size_t)row0 * W + i;
-        float v = res[i].x * q.norm;
-        if (q.res) v += q.res_coef * q.res[g];
-        if (q.img_scale) v *= q.img_scale[(row0 + r) / q.rows_per_image];
-        q.out[g] = v;
+    for (int i = threadIdx.x; i < S * M; i += blockDim.x) {
+        const int r = i / M, k = i - r * M;
+        const float2 xk = b[r * (M + 1) + k], xc = b[r * (M + 1) + (M - k)];
+        const float ex = 0.5f * (xk.x + xc.x), ey = 0.5f * (xk.y - xc.y);
+        const float tx = 0.5f * (xk.x - xc.x), ty = 0.5f * (xk.y + xc.y);     // T = (X[k] - conj X[M-k]) / 2
+        const float2 w = twW[k];                                               // O = conj(w) T
+        const float ox = w.x * tx + w.y * ty, oy = w.x * ty - w.y * tx;
+        a[r * M + k] = make_float2(ex - oy, ey + ox);                          // E + i O
+    }
+    __syncthreads();
+    float2* res = fft_smem<1>(PM, a, b, S, M, 1);
+    const float nrm = 2.0f * q.norm;                                           // IDFT_M gives (W/2) x
+    float2* dst = reinterpret_cast<float2*>(q.out + (size_t)row0 * 2 * M);
+    const float2* rsrc = q.res ? reinterpret_cast<const float2*>(q.res + (size_t)row0 * 2 * M) : nullptr;
+    for (int i = threadIdx.x; i < S * M; i += blockDim.x) {
+        const int r = i / M;
+        float2 v = make_float2(res[i].x * nrm, res[i].y * nrm);
+        if (rsrc) { const float2 t = rsrc[i]; v.x += q.res_coef * t.x; v.y += q.res_coef * t.y; }
+        if (q.img_scale) { const float sc = q.img_scale[(row0 + r) / q.rows_per_image]; v.x *= sc; v.y *= sc; }
+        dst[i] = v;
     }
 }
 
@@ -473,8 +494,8 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
-static int rows_per_cta_for(int W) { return max(1, min(8, 4096 / W)); }
-static size_t rows_smem(int W, int rpc) { return (size_t)2 * rpc * W * sizeof(float2); }
+static int rows_per_cta_for(int W) { return max(1, min(16, 8192 / W)); }              // ~4096 packed complex points per CTA
+static size_t rows_smem(int W, int rpc) { return (size_t)2 * rpc * (W / 2 + 1) * sizeof(float2); }
 static int cols_per_cta_for(int H) {
     int tc = 8;
     while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;
@@ -503,20 +524,23 @@ FDN_API int fdn_fft_prepare(int H, int W) {
     FDN_REQUIRE(H >= 1 && W >= 2, "bad FFT size");
     FDN_REQUIRE(fdn_fft_get_plan(H, &p) == 0, "plan creation failed");
     FDN_REQUIRE(fdn_fft_get_plan(W, &p) == 0, "plan creation failed");
+    if (W % 2 == 0) FDN_REQUIRE(fdn_fft_get_plan(W / 2, &p) == 0, "plan creation failed");
     return 0;
 }
 
 // x [planes][H][W] real -> spec [planes][H][W/2+1] complex (interleaved re,im).  Rows pass only.
 FDN_API int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int W, cudaStream_t st) {
     FDN_REQUIRE(x && spec && planes > 0 && H > 0 && W >= 2, "bad arguments");
-    FftPlanDev P;
-    FDN_REQUIRE(fdn_fft_get_plan(W, &P) == 0, "plan creation failed");
+    FDN_REQUIRE(W % 2 == 0, "the real-packed row transform needs an even width");
+    FDN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0, "x must be 8-byte aligned");
+    FftPlanDev PM, PW;
+    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM) == 0 && fdn_fft_get_plan(W, &PW) == 0, "plan creation failed");
     int rpc = rows_per_cta_for(W);
     size_t smem = rows_smem(W, rpc);
     int rc = set_smem(k_rows_r2c, smem);
     if (rc) return rc;
     int nrows = planes * H;
-    FDN_LAUNCH(k_rows_r2c, dim3(fdn_cdiv(nrows, rpc)), dim3(256), smem, st, x, reinterpret_cast<float2*>(spec), P, nrows, rpc);
+    FDN_LAUNCH(k_rows_r2c, dim3(fdn_cdiv(nrows, rpc)), dim3(256), smem, st, x, reinterpret_cast<float2*>(spec), PM, PW.tw, nrows, rpc);
     return fdn_check_launch("k_rows_r2c");
 }
 
@@ -524,8 +548,10 @@ FDN_API int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int
 FDN_API int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int W, float inv_norm, const float* res,
                              float res_coef, const float* img_scale, int planes_per_image, cudaStream_t st) {
     FDN_REQUIRE(spec && y && planes > 0 && H > 0 && W >= 2, "bad arguments");
-    FftPlanDev P;
-    FDN_REQUIRE(fdn_fft_get_plan(W, &P) == 0, "plan creation failed");
+    FDN_REQUIRE(W % 2 == 0, "the real-packed row transform needs an even width");
+    FDN_REQUIRE((reinterpret_cast<uintptr_t>(y) & 7) == 0 && (!res || (reinterpret_cast<uintptr_t>(res) & 7) == 0), "y/res must be 8-byte aligned");
+    FftPlanDev PM, PW;
+    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM) == 0 && fdn_fft_get_plan(W, &PW) == 0, "plan creation failed");
     RowsC2RParams q;
     q.in = reinterpret_cast<const float2*>(spec);
     q.out = y;
@@ -539,7 +565,7 @@ FDN_API int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int
     size_t smem = rows_smem(W, q.rows_per_cta);
     int rc = set_smem(k_rows_c2r, smem);
     if (rc) return rc;
-    FDN_LAUNCH(k_rows_c2r, dim3(fdn_cdiv(q.nrows, q.rows_per_cta)), dim3(256), smem, st, q, P);
+    FDN_LAUNCH(k_rows_c2r, dim3(fdn_cdiv(q.nrows, q.rows_per_cta)), dim3(256), smem, st, q, PM, PW.tw);
     return fdn_check_launch("k_rows_c2r");
 }
 

@@ -62,6 +62,23 @@ __global__ void __launch_bounds__(128) k_fdffn_patch(const float* __restrict__ x
     store_patch(out + off, W, p);
 }
 
+// One bin of the FDSA algebra.  Moduli use the hardware reciprocal square root (2 ulp): they only scale magnitudes,
+// the phases come from exact complex products of the clamped inputs.  replace_denormals keeps every modulus >= 1.4e-10.
+__device__ __forceinline__ float2 fdsa_bin(float2 q, float2 k, float2 v, int role) {
+    float2 qk = cmul(q, k);
+    qk.x = fdn_rd(qk.x);
+    qk.y = fdn_rd(qk.y);
+    const float A = sqrtf(qk.x * qk.x + qk.y * qk.y);                       // |rd(q k)|
+    const float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
+    const float iq = rsqrtf(qc.x * qc.x + qc.y * qc.y), ik = rsqrtf(kc.x * kc.x + kc.y * kc.y);
+    const float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));   // e^{i(th_q - th_k)}
+    const float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));                 // v' = rd(v * fft)
+    const float sv = vc.x * vc.x + vc.y * vc.y, iv = rsqrtf(sv);
+    if (role == 0) { const float m = sv * iv; return make_float2(m * u.x, m * u.y); }      // |v'| e^{i dtheta}
+    if (role == 1) { const float s = A * iv; return make_float2(s * vc.x, s * vc.y); }      // |qk| e^{i angle v'}
+    return make_float2(A * u.x, A * u.y);                                                   // |qk| e^{i dtheta}
+}
+
 // ---------------------------------------------------------------------------------------------------
 // FDSA: three lanes (q, k, v roles) cooperate on one (channel, patch); bins are exchanged with shuffles
 // ---------------------------------------------------------------------------------------------------
@@ -102,23 +119,7 @@ __global__ void __launch_bounds__(128) k_fdsa_patch(const float* __restrict__ hi
             float2 q = make_float2(__shfl_sync(0xffffffffu, sx, l0), __shfl_sync(0xffffffffu, sy, l0));
             float2 k = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 1), __shfl_sync(0xffffffffu, sy, l0 + 1));
             float2 v = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 2), __shfl_sync(0xffffffffu, sy, l0 + 2));
-            // |rd(q k)|
-            float2 qk = cmul(q, k);
-            qk.x = fdn_rd(qk.x);
-            qk.y = fdn_rd(qk.y);
-            float A = sqrtf(qk.x * qk.x + qk.y * qk.y);
-            // unit phasor e^{i(angle rd(q) - angle rd(k))}
-            float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
-            float iq = 1.0f / sqrtf(qc.x * qc.x + qc.y * qc.y), ik = 1.0f / sqrtf(kc.x * kc.x + kc.y * kc.y);
-            float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));
-            // v' = rd(v * fft), m = |v'|
-            float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));
-            float m = sqrtf(vc.x * vc.x + vc.y * vc.y);
-            float2 o;
-            if (role == 0) o = make_float2(m * u.x, m * u.y);                      // |v'| e^{i dtheta}
-            else if (role == 1) { float s = A / m; o = make_float2(s * vc.x, s * vc.y); }   // |qk| e^{i angle v'}
-            else o = make_float2(A * u.x, A * u.y);                                // |qk| e^{i dtheta}
-            S[ky][kx] = o;
+            S[ky][kx] = fdsa_bin(q, k, v, role);
         }
     irfft2_8x8(S, p);
     if (valid) store_patch(out + off_out, W, p);
@@ -210,20 +211,7 @@ __global__ void __launch_bounds__(128) k_fdsa_patch_dw(const float* __restrict__
             float2 q = make_float2(__shfl_sync(0xffffffffu, sx, l0), __shfl_sync(0xffffffffu, sy, l0));
             float2 k = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 1), __shfl_sync(0xffffffffu, sy, l0 + 1));
             float2 v = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 2), __shfl_sync(0xffffffffu, sy, l0 + 2));
-            float2 qk = cmul(q, k);
-            qk.x = fdn_rd(qk.x);
-            qk.y = fdn_rd(qk.y);
-            float A = sqrtf(qk.x * qk.x + qk.y * qk.y);
-            float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
-            float iq = 1.0f / sqrtf(qc.x * qc.x + qc.y * qc.y), ik = 1.0f / sqrtf(kc.x * kc.x + kc.y * kc.y);
-            float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));
-            float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));
-            float m = sqrtf(vc.x * vc.x + vc.y * vc.y);
-            float2 o;
-            if (role == 0) o = make_float2(m * u.x, m * u.y);
-            else if (role == 1) { float s = A / m; o = make_float2(s * vc.x, s * vc.y); }
-            else o = make_float2(A * u.x, A * u.y);
-            S[ky][kx] = o;
+            S[ky][kx] = fdsa_bin(q, k, v, role);
         }
     irfft2_8x8(S, p);
     if (valid && role != 3) store_patch(out + off_out, W, p);

@@ -6,11 +6,12 @@
 // FDSA to_hidden / project_out, FDFFN project_in / project_out, FCAFFN project_in / project_out, Fuse conv / conv2
 // (FDN_arch.py:388-389, 451-452, 562, 566, 685-686).
 //
-// Persistent, warp-specialised kernel (18 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
-//   warp  17    loader: streams raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
-//               into a shared-memory ring with cp.async.bulk (TMA bulk copies, 512 contiguous bytes per channel row)
-//               completing on mbarrier transaction counts - several tiles ahead of the consumers, which is what keeps
-//               enough bytes in flight to cover HBM latency
+// Persistent, warp-specialised kernel (20 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
+//   warps 17-19 loaders: stream raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
+//               into a shared-memory ring with 16-byte cp.async copies whose completion arrives on the slot's mbarrier
+//               (cp.async.mbarrier.arrive) - several tiles ahead of the consumers, which keeps enough bytes in flight to
+//               cover HBM latency.  (One cp.async.bulk per 512-byte channel row was measured to be request-rate bound
+//               in the TMA unit for K > 64.)
 //   warps 0-7   producers: two threads per pixel; take the LayerNorm statistics from shared memory (two-pass mean /
 //               biased variance like the reference), apply the per-pixel prologue, split each value into tf32 hi + lo
 //               and store it into the canonical K-major SWIZZLE_128B operand stage
@@ -36,8 +37,9 @@
 #define MMA_EPI_WARP0 8
 #define MMA_EPI_THREADS 256
 #define MMA_MMA_WARP 16
-#define MMA_LOAD_WARP 17
-#define MMA_THREADS 576
+#define MMA_LOAD_WARP0 17     // three loader warps
+#define MMA_LOAD_THREADS 96
+#define MMA_THREADS 640
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
@@ -70,7 +72,10 @@ struct PwMmaParams {
     int nstage;             // operand stages (1 or 2)
     int ring;               // raw ring slots
     int nmain;              // main accumulators (K blocks round-robin)
-    int tmem_cols;          // power of two >= (nmain + (passes==3)) * Nc
+    int tmem_cols;          // power of two >= nbuf * (nmain + ncorr) * Nc
+    int ncorr;              // 1 when the corrections have their own accumulator
+    int nbuf;               // accumulator sets (2 = the epilogue of tile t overlaps the MMAs of tile t+1)
+    int bulk;               // 1: one cp.async.bulk per 512-byte channel row (few rows per tile), 0: 16-byte cp.async by 128 threads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +112,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier receives this thread's arrival once all of its prior cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -134,14 +146,15 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
 }
 __device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// issue only; call tmem_ld_wait() before using the registers
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ const float* src_row(const PwMmaParams& q, int b, int k) {
     if (k < q.C0) return q.src0 + ((size_t)b * q.C0 + k) * q.HW;
@@ -169,9 +182,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     uint64_t* raw_empty = raw_full + MMA_MAX_RING;
     uint64_t* a_full = raw_empty + MMA_MAX_RING;
     uint64_t* a_empty = a_full + 2;
-    uint64_t* acc_full = a_empty + 2;
-    uint64_t* acc_empty = acc_full + 1;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* acc_full = a_empty + 2;        // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.y;
@@ -183,10 +196,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const int gsize = PRO == 2 ? q.K / 3 : q.K;
 
     if (tid == 0) {
-        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
+        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : MMA_LOAD_THREADS); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
         for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS); mbar_init(&a_empty[i], 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, MMA_EPI_THREADS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_MMA_WARP) {
@@ -212,34 +224,69 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const uint32_t tmem_base = *s_tmem;
     const int nmain = q.nmain;
 
-    if (warp == MMA_LOAD_WARP) {
-        // =============================================== loader =====================================================
-        // all 32 lanes issue bulk copies (one channel row each); lane 0 arms the transaction count first
+    if (warp >= MMA_LOAD_WARP0) {
+        // =============================================== loaders ====================================================
+        // 128 threads stream 16-byte pieces with cp.async (L2 -> shared memory, no registers); each thread's arrival on
+        // raw_full[r] is deferred by the hardware until its copies have landed
+        const int lt = tid - MMA_LOAD_WARP0 * 32;
         uint32_t lit = 0;
+        if (q.bulk) {
+            // few channel rows per tile: one TMA bulk copy (512 contiguous bytes) per row, issued by the lanes of one warp
+            if (warp == MMA_LOAD_WARP0)
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
+                    const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;
+                    for (int kb = 0; kb < nkb; ++kb, ++lit) {
+                        const int r = lit % q.ring;
+                        if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
+                        unsigned char* slot = s_raw + (size_t)r * slot_bytes;
+                        const int rows = min(MMA_KB, q.K - kb * MMA_KB);
+                        if (lane == 0) {
+                            uint32_t bytes = (uint32_t)rows * len * (has_aux ? 2 : 1);
+                            if (PRO == 2 && kb == 0) bytes += 6 * len;
+                            mbar_expect_tx(&raw_full[r], bytes);
+                        }
+                        __syncwarp();
+                        if (lane < rows) {
+                            const int k = kb * MMA_KB + lane;
+                            bulk_g2s(slot + lane * (MMA_TP * 4), src_row(q, b, k) + p0, len, &raw_full[r]);
+                            if (has_aux) {
+                                const int ka = PRO == 2 ? k % gsize : k;
+                                bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0, len, &raw_full[r]);
+                            }
+                        }
+                        if (PRO == 2 && kb == 0 && lane < 6)
+                            bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
+                    }
+                }
+        } else
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
-            const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;          // bytes per channel row (multiple of 16)
+            const int vch = min(MMA_TP, HW - p0) >> 2;                        // valid 16-byte pieces per channel row
             for (int kb = 0; kb < nkb; ++kb, ++lit) {
                 const int r = lit % q.ring;
                 if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
                 unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                 const int rows = min(MMA_KB, q.K - kb * MMA_KB);
-                if (lane == 0) {
-                    uint32_t bytes = (uint32_t)rows * len * (has_aux ? 2 : 1);
-                    if (PRO == 2 && kb == 0) bytes += 6 * len;
-                    mbar_expect_tx(&raw_full[r], bytes);
-                }
-                __syncwarp();
-                if (lane < rows) {
-                    const int k = kb * MMA_KB + lane;
-                    bulk_g2s(slot + lane * (MMA_TP * 4), src_row(q, b, k) + p0, len, &raw_full[r]);
-                    if (has_aux) {
-                        const int ka = PRO == 2 ? k % gsize : k;
-                        bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0, len, &raw_full[r]);
+                for (int i = lt; i < rows * 32; i += MMA_LOAD_THREADS) {
+                    const int row = i >> 5, ch = i & 31;
+                    if (ch < vch) {
+                        const int k = kb * MMA_KB + row;
+                        cp_async16(slot + row * (MMA_TP * 4) + ch * 16, src_row(q, b, k) + p0 + ch * 4);
+                        if (has_aux) {
+                            const int ka = PRO == 2 ? k % gsize : k;
+                            cp_async16(slot + MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16,
+                                       q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0 + ch * 4);
+                        }
                     }
                 }
-                if (PRO == 2 && kb == 0 && lane < 6)
-                    bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
+                if (PRO == 2 && kb == 0)
+                    for (int i = lt; i < 6 * 32; i += MMA_LOAD_THREADS) {
+                        const int row = i >> 5, ch = i & 31;
+                        if (ch < vch)
+                            cp_async16(slot + 2 * MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16, q.stats + ((size_t)b * 6 + row) * HW + p0 + ch * 4);
+                    }
+                cp_async_arrive(&raw_full[r]);
             }
         }
     } else if (warp < MMA_EPI_WARP0) {
@@ -300,28 +347,35 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 unsigned char* stage = s_stage + s * stage_bytes;
                 const int kleft = q.K - kb * MMA_KB;                      // valid channels in this block (may exceed 32)
                 const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
-                const float* gam = s_gam + kb * MMA_KB;
-                const float* bet = s_bet + kb * MMA_KB;
                 if (it >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((it / q.nstage) - 1) & 1);
+                // a 32-channel block touches at most two LayerNorm groups (PRO 2): [0, kbnd) -> g_lo, the rest -> g_lo + 1
+                const int g_lo = PRO == 2 ? (kb * MMA_KB) / gsize : 0;
+                const int kbnd = PRO == 2 ? (g_lo + 1) * gsize - kb * MMA_KB : 0;
+                const float gm_a = g_lo == 0 ? gmu0 : (g_lo == 1 ? gmu1 : gmu2), gr_a = g_lo == 0 ? grs0 : (g_lo == 1 ? grs1 : grs2);
+                const float gm_b = g_lo == 0 ? gmu1 : gmu2, gr_b = g_lo == 0 ? grs1 : grs2;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = half + 2 * i;
                     if (c < nchunks_used) {
                         float hi[4], lo[4];
+                        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+                        if (PRO != 0) {
+                            g4 = *reinterpret_cast<const float4*>(s_gam + kb * MMA_KB + 4 * c);
+                            b4 = *reinterpret_cast<const float4*>(s_bet + kb * MMA_KB + 4 * c);
+                        }
+                        const float gj[4] = {g4.x, g4.y, g4.z, g4.w}, bj[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int kk = 4 * c + j;
                             float x = raw[kk * MMA_TP];
                             if (PRO == 1) {
-                                x = (x - mu) * rs * gam[kk] + bet[kk];
+                                x = (x - mu) * rs * gj[j] + bj[j];
                             } else if (PRO == 2) {
-                                const int g = (kb * MMA_KB + kk) / gsize;
-                                const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2);
-                                const float gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
-                                x = ((x - gm) * gr * gam[kk] + bet[kk]) * raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
+                                const float gm = kk < kbnd ? gm_a : gm_b, gr = kk < kbnd ? gr_a : gr_b;
+                                x = ((x - gm) * gr * gj[j] + bj[j]) * raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
                             } else if (PRO == 3) {
                                 const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
-                                x = ((x - mu) * rs * gam[kk] + bet[kk]) * x1 + x1;
+                                x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
                             }
                             if (!pvalid || kk >= kleft) x = 0.f;
                             hi[j] = to_tf32(x);
@@ -344,8 +398,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     } else if (warp == MMA_MMA_WARP) {
         // =============================================== MMA issuer ================================================
         uint32_t it = 0, titer = 0;
+        const uint32_t set_cols = (uint32_t)((nmain + q.ncorr) * q.Nc);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
-            if (titer >= 1) mbar_wait(acc_empty, (titer - 1) & 1);        // the epilogue has drained the accumulators
+            const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
+            const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;          // how often this accumulator set was used before
+            if (use >= 1) mbar_wait(&acc_empty[buf], (use - 1) & 1);           // the epilogue has drained this accumulator set
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool corr_started = false;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -357,19 +414,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     const uint32_t b_hi = q.b_resident ? smem_u32(s_bres) + (uint32_t)kb * 2 * b_bytes : a_hi + 2 * a_bytes;
                     const uint32_t b_lo = b_hi + b_bytes;
                     const int ksteps = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 3;
-                    const uint32_t d_main = tmem_base + (uint32_t)((kb % nmain) * q.Nc);
-                    const uint32_t d_corr = tmem_base + (uint32_t)(nmain * q.Nc);
+                    const uint32_t d_main = tmem_base + buf * set_cols + (uint32_t)((kb % nmain) * q.Nc);
+                    const uint32_t d_corr = q.ncorr ? tmem_base + buf * set_cols + (uint32_t)(nmain * q.Nc) : d_main;
                     for (int t = 0; t < ksteps; ++t) {
                         const uint32_t koff = (uint32_t)t * 32;       // 8 tf32 = 32 bytes along K inside the swizzle atom
                         umma_tf32(d_main, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc, (kb >= nmain || t > 0) ? 1u : 0u);
                         if (PASSES == 3) {
-                            umma_tf32(d_corr, make_desc(a_hi + koff), make_desc(b_lo + koff), q.idesc, corr_started ? 1u : 0u);
+                            umma_tf32(d_corr, make_desc(a_hi + koff), make_desc(b_lo + koff), q.idesc, (corr_started || !q.ncorr) ? 1u : 0u);
                             umma_tf32(d_corr, make_desc(a_lo + koff), make_desc(b_hi + koff), q.idesc, 1u);
                             corr_started = true;
                         }
                     }
                     umma_commit(&a_empty[s]);
-                    if (kb == nkb - 1) umma_commit(acc_full);
+                    if (kb == nkb - 1) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
             }
@@ -387,45 +444,50 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         const float res_coef = q.res_coef;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t titer = 0;
+        const uint32_t set_cols = (uint32_t)((nmain + q.ncorr) * q.Nc);
+        // residual of this warp's first 16-column group, fetched one tile ahead so its HBM latency is hidden behind a tile
+        float rnext[16];
+        auto prefetch_res = [&](int tile_n) {
+            const int bn = tile_n / tiles_per_img, pn = (tile_n - bn * tiles_per_img) * MMA_TP + row;
+            const bool ok = has_res && tile_n < ntiles && pn < HW && c16_begin < c16_end;
+            const float* rp = q.res + ((size_t)bn * q.N + (size_t)chunk * q.Nc + c16_begin * 16) * HW + (ok ? pn : 0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rnext[j] = (ok && chunk * q.Nc + c16_begin * 16 + j < q.N) ? rp[(size_t)j * HW] : 0.f;
+        };
+        prefetch_res(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
             const int pe = p0 + row;
             const bool valid = pe < HW;
             const size_t base = ((size_t)b * q.N + (size_t)chunk * q.Nc) * HW + (valid ? pe : 0);
-            // prefetch the residual of this warp's first 16 output channels while the MMAs of this tile are still running
+            const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
+            const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;
+            const uint32_t tacc = tlane + buf * set_cols;
             float rpre[16];
-            if (has_res) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int nl = c16_begin * 16 + j;
-                    rpre[j] = (valid && c16_begin < c16_end && chunk * q.Nc + nl < q.N) ? q.res[base + (size_t)nl * HW] : 0.f;
-                }
-            }
-            mbar_wait(acc_full, titer & 1);
+            for (int j = 0; j < 16; ++j) rpre[j] = rnext[j];
+            prefetch_res(tile + gridDim.x);
+            mbar_wait(&acc_full[buf], use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int c16 = c16_begin; c16 < c16_end; ++c16) {
                 float acc[16];
                 {
                     uint32_t r[16];
-                    tmem_ld16(tlane + (uint32_t)(c16 * 16), r);
+                    tmem_ld16(tacc + (uint32_t)(c16 * 16), r);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
                 }
-                for (int a = 1; a < nused; ++a) {
+                for (int a = 1; a < nused + q.ncorr; ++a) {      // remaining main accumulators, then the correction accumulator
                     uint32_t r[16];
-                    tmem_ld16(tlane + (uint32_t)(a * q.Nc + c16 * 16), r);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
-                }
-                if (PASSES == 3) {
-                    uint32_t r[16];
-                    tmem_ld16(tlane + (uint32_t)(nmain * q.Nc + c16 * 16), r);
+                    tmem_ld16(tacc + (uint32_t)((a < nused ? a : nmain) * q.Nc + c16 * 16), r);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
                 }
                 if (c16 == c16_end - 1) {        // this warp's TMEM reads of the tile are complete: hand the accumulators back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(acc_empty);
+                    mbar_arrive(&acc_empty[buf]);
                 }
                 const int n0 = chunk * q.Nc + c16 * 16;
                 if (valid) {
@@ -459,7 +521,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             }
             if (c16_begin >= c16_end) {          // a warp without columns (Nc == 16) still takes part in the hand-back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(acc_empty);
+                mbar_arrive(&acc_empty[buf]);
             }
         }
     }
@@ -494,7 +556,7 @@ struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
     const size_t slot = (size_t)MMA_SLOT_BYTES * (prologue >= 2 ? 2 : 1) + (prologue == 2 ? 6 * MMA_TP * 4 : 0);
-    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 6) * sizeof(uint64_t) + 64;
+    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 8) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
     const int ring_min = (prologue == 1 || prologue == 3) ? max(nkb, 2) : 2;  // LN needs all K blocks of a tile resident
     PwMmaPlan best;
@@ -573,12 +635,19 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     PwMmaPlan plan;
     FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, &plan), "tile does not fit in shared memory");
     q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
-    const int ncorr = passes == 3 ? 1 : 0;
+    // accumulators: one K block (<= 12 accumulations) needs no split; longer K keeps hi*hi and the corrections apart and
+    // spreads the K blocks over up to three main accumulators
+    q.ncorr = (passes == 3 && nkb >= 2) ? 1 : 0;
     q.nmain = 1;
-    if (nkb >= 2) q.nmain = min(min(3, nkb), (512 / Nc) - ncorr);
-    if (q.nmain < 1) q.nmain = 1;
+    if (nkb >= 2) q.nmain = max(1, min(min(3, nkb), (512 / Nc) - q.ncorr));
+    const int set_cols = (q.nmain + q.ncorr) * Nc;
+    q.nbuf = 2 * set_cols <= 512 ? 2 : 1;
+    // copy requests per tile: the TMA unit handles ~1 small bulk request per 64 cycles, so many-row tiles use cp.async instead
+    q.bulk = (q.K * (prologue >= 2 ? 2 : 1) + (prologue == 2 ? 6 : 0)) <= 100 ? 1 : 0;
+    if (const char* e = getenv("FDN_MMA_NBUF")) { if (atoi(e) == 1) { q.nbuf = 1; q.tmem_cols = 32; while (q.tmem_cols < set_cols) q.tmem_cols <<= 1; } }
+    if (const char* e = getenv("FDN_MMA_BULK")) q.bulk = atoi(e);
     q.tmem_cols = 32;
-    while (q.tmem_cols < (q.nmain + ncorr) * Nc) q.tmem_cols <<= 1;
+    while (q.tmem_cols < q.nbuf * set_cols) q.tmem_cols <<= 1;
     FDN_REQUIRE(q.tmem_cols <= 512, "accumulators do not fit in tensor memory");
     FDN_REQUIRE(nkb * MMA_KB <= MMA_MAX_K, "too many input channels");
     static int num_sms = 0;
