@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const int gsize = PRO == 2 ? q.K / 3 : q.K;
 
     if (tid == 0) {
-        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : MMA_LOAD_THREADS); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
-        for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
+        for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS + (q.b_resident ? 0 : 1)); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -230,7 +230,21 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         // raw_full[r] is deferred by the hardware until its copies have landed
         const int lt = tid - MMA_LOAD_WARP0 * 32;
         uint32_t lit = 0;
-        if (q.bulk) {
+        if (!q.b_resident && warp == MMA_LOAD_WARP0 + 2) {
+            // weight panels that do not fit in shared memory: one contiguous TMA bulk copy per K block straight into the
+            // operand stage (the packed image is contiguous in global memory); completion counts on a_full[s]
+            if (lane == 0) {
+                uint32_t bit = 0;
+                const uint32_t bytes = (uint32_t)panels * b_bytes;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                    for (int kb = 0; kb < nkb; ++kb, ++bit) {
+                        const int s = bit % q.nstage;
+                        if (bit >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((bit / q.nstage) - 1) & 1);
+                        mbar_expect_tx(&a_full[s], bytes);
+                        bulk_g2s(s_stage + s * stage_bytes + 2 * a_bytes, bsrc + (size_t)kb * 2 * q.Nc * 32, bytes, &a_full[s]);
+                    }
+            }
+        } else if (q.bulk) {
             // few channel rows per tile: one TMA bulk copy (512 contiguous bytes) per row, issued by the lanes of one warp
             if (warp == MMA_LOAD_WARP0)
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -259,7 +273,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                             bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
                     }
                 }
-        } else
+        } else {
+        const int lthreads = q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32;      // the last loader warp may stream weights
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
             const int vch = min(MMA_TP, HW - p0) >> 2;                        // valid 16-byte pieces per channel row
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
                 unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                 const int rows = min(MMA_KB, q.K - kb * MMA_KB);
-                for (int i = lt; i < rows * 32; i += MMA_LOAD_THREADS) {
+                for (int i = lt; i < rows * 32; i += lthreads) {
                     const int row = i >> 5, ch = i & 31;
                     if (ch < vch) {
                         const int k = kb * MMA_KB + row;
@@ -281,13 +296,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     }
                 }
                 if (PRO == 2 && kb == 0)
-                    for (int i = lt; i < 6 * 32; i += MMA_LOAD_THREADS) {
+                    for (int i = lt; i < 6 * 32; i += lthreads) {
                         const int row = i >> 5, ch = i & 31;
                         if (ch < vch)
                             cp_async16(slot + 2 * MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16, q.stats + ((size_t)b * 6 + row) * HW + p0 + ch * 4);
                     }
                 cp_async_arrive(&raw_full[r]);
             }
+        }
         }
     } else if (warp < MMA_EPI_WARP0) {
         // =============================================== producers =================================================
@@ -386,11 +402,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     }
                 }
                 mbar_arrive(&raw_empty[r]);            // this thread is done with the raw slot
-                if (!q.b_resident) {
-                    const float4* src = reinterpret_cast<const float4*>(bsrc + (size_t)kb * 2 * q.Nc * 32);
-                    float4* dst = reinterpret_cast<float4*>(stage + 2 * a_bytes);
-                    for (int i = tid; i < panels * q.Nc * 8; i += MMA_PROD_THREADS) dst[i] = src[i];
-                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&a_full[s]);
             }
@@ -568,9 +579,13 @@ static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
             int ring = (int)((budget - fixed) / slot);
             if (ring > MMA_MAX_RING) ring = MMA_MAX_RING;
             PwMmaPlan p{resident, nstage, ring, fixed + ring * slot};
-            // prefer: deep ring (>= 4 slots beyond the minimum is plenty), then residency, then two stages
-            const int score = min(ring - ring_min, 3) * 4 + resident * 2 + (nstage - 1);
-            const int best_score = found ? min(best.ring - ring_min, 3) * 4 + best.resident * 2 + (best.nstage - 1) : -1;
+            // prefer a resident weight (no per-tile weight traffic, all loader warps stream activations) as long as the
+            // ring can still prefetch one K block beyond the minimum; then the deeper ring; then two operand stages
+            auto score_of = [&](const PwMmaPlan& c) {
+                return (c.resident && c.ring >= ring_min + 1 ? 100 : 0) + min(c.ring - ring_min, 4) * 4 + c.resident * 2 + (c.nstage - 1);
+            };
+            const int score = score_of(p);
+            const int best_score = found ? score_of(best) : -1;
             if (score > best_score) { best = p; found = true; }
         }
     if (found) *out = best;
