@@ -255,11 +255,18 @@ def _fdffn(cx, x, p):
     hid = _new(x, b, hd, h, w)
     _conv1x1(cx, [x], p + "ffn.project_in.weight", hid, ln=cx.ln(p + "norm2."))
     s1 = _new(x, b, hd, h, w)
-    ops.dwconv3(hid, cx.flat(p + "ffn.space.0.weight"), s1, mode=1)
-    s2 = _new(x, b, hd, h, w)
-    ops.dwconv3(s1, cx.flat(p + "ffn.space.2.weight"), s2, mode=0)
-    ops.fdffn_patch(hid, s2, cx.ffn_spec(p + "ffn."), s1)          # s1 <- spectral branch + spatial branch
-    ops.dwconv3(s1, cx.flat(p + "ffn.dwconv.weight"), s2, mode=2)  # s2 <- gated
+    if os.environ.get("FDN_B200_FDFFN_FUSED") == "1":
+        # dw3x3 -> GELU -> dw3x3 in shared-memory tiles + the 8x8 patch-FFT branch + their sum in one kernel.  Measured on
+        # B200 (r1): 84.6 ms vs 43 ms per 4 images for the three kernels below - the halo recompute of erf-GELU and the
+        # half-idle FFT phase make it compute-bound while the unfused kernels stream at ~3.5 TB/s - so it is opt-in.
+        ops.fdffn_spatial(hid, cx.flat(p + "ffn.space.0.weight"), cx.flat(p + "ffn.space.2.weight"), cx.ffn_spec(p + "ffn."), s1)
+        s2 = hid
+    else:
+        ops.dwconv3(hid, cx.flat(p + "ffn.space.0.weight"), s1, mode=1)
+        s2 = _new(x, b, hd, h, w)
+        ops.dwconv3(s1, cx.flat(p + "ffn.space.2.weight"), s2, mode=0)
+        ops.fdffn_patch(hid, s2, cx.ffn_spec(p + "ffn."), s1)      # s1 <- spectral branch + spatial branch
+    ops.dwconv3(s1, cx.flat(p + "ffn.dwconv.weight"), s2, mode=2)  # s2 <- gelu(x1) * x2
     out = _new(x, b, c, h, w)
     _conv1x1(cx, [s2], p + "ffn.project_out.weight", out, res=x)
     return out

@@ -218,6 +218,106 @@ __global__ void __launch_bounds__(128) k_fdsa_patch_dw(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FDFFN spatial + spectral branches in one kernel (FDN_arch.py:457-470):
+//     t = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec)
+// A CTA owns a 32x32 pixel tile of 8 channels.  The tile of h (halo 2) is staged in shared memory once; s1 = gelu(dw_a(h))
+// is produced on the 34x34 ring it is needed on (zero outside the image, as the second conv's padding sees it), s2 = dw_b(s1)
+// on the 32x32 tile; then one thread per (channel, 8x8 patch) runs the register FFT on h's centre and adds s2.  Replaces
+// three kernels and five of the seven tensor round trips of the unfused sequence.
+// ---------------------------------------------------------------------------------------------------
+#define FS_T 32
+#define FS_C 8
+#define FS_HP (FS_T + 4)   // h tile edge
+#define FS_SP (FS_T + 2)   // s1 tile edge
+
+__global__ void __launch_bounds__(256, 2) k_fdffn_spatial(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ wb,
+                                                          const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W) {
+    FDN_DYN_SMEM(smem);
+    float* sh = reinterpret_cast<float*>(smem);                 // [FS_C][FS_HP][FS_HP]
+    float* s1 = sh + FS_C * FS_HP * FS_HP;                      // [FS_C][FS_SP][FS_SP]
+    float* s2 = s1 + FS_C * FS_SP * FS_SP;                      // [FS_C][FS_T][FS_T]
+    const int tiles_x = (W + FS_T - 1) / FS_T;
+    const int x0 = (blockIdx.x % tiles_x) * FS_T, y0 = (blockIdx.x / tiles_x) * FS_T;
+    const int c0 = blockIdx.y * FS_C, b = blockIdx.z;
+    const int nc = min(FS_C, C - c0);
+    const int tid = threadIdx.x;
+    // ---- stage h with a halo of 2 (zero outside the image)
+    for (int i = tid; i < nc * FS_HP * FS_HP; i += 256) {
+        const int c = i / (FS_HP * FS_HP), r = i - c * (FS_HP * FS_HP);
+        const int yy = r / FS_HP, xx = r - yy * FS_HP;
+        const int gy = y0 + yy - 2, gx = x0 + xx - 2;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = h[(((size_t)b * C + c0 + c) * H + gy) * W + gx];
+        sh[i] = v;
+    }
+    __syncthreads();
+    // ---- s1 = gelu(dw_a(h)) on the 34x34 ring, zero outside the image
+    for (int i = tid; i < nc * FS_SP * FS_SP; i += 256) {
+        const int c = i / (FS_SP * FS_SP), r = i - c * (FS_SP * FS_SP);
+        const int yy = r / FS_SP, xx = r - yy * FS_SP;
+        const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const float* k = wa + (c0 + c) * 9;
+            const float* p = sh + c * FS_HP * FS_HP + yy * FS_HP + xx;     // top-left of the 3x3 window
+            float a = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * p[dy * FS_HP + dx];
+            v = fdn_gelu(a);
+        }
+        s1[i] = v;
+    }
+    __syncthreads();
+    // ---- s2 = dw_b(s1) on the tile
+    for (int i = tid; i < nc * FS_T * FS_T; i += 256) {
+        const int c = i / (FS_T * FS_T), r = i - c * (FS_T * FS_T);
+        const int yy = r / FS_T, xx = r - yy * FS_T;
+        const float* k = wb + (c0 + c) * 9;
+        const float* p = s1 + c * FS_SP * FS_SP + yy * FS_SP + xx;
+        float a = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * p[dy * FS_SP + dx];
+        s2[i] = a;
+    }
+    __syncthreads();
+    // ---- spectral branch per (channel, patch) + sum
+    if (tid < nc * 16) {
+        const int c = tid >> 4, pt = tid & 15;
+        const int py = pt >> 2, px = pt & 3;
+        const int gy = y0 + py * 8, gx = x0 + px * 8;
+        if (gy < H && gx < W) {
+            float p[64];
+            float2 S[8][5];
+            const float* src = sh + c * FS_HP * FS_HP + (py * 8 + 2) * FS_HP + px * 8 + 2;
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+#pragma unroll
+                for (int x = 0; x < 8; ++x) p[8 * y + x] = src[y * FS_HP + x];
+            rfft2_8x8(p, S);
+            const float2* w = wspec + (c0 + c) * 40;
+#pragma unroll
+            for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    float2 z = make_float2(fdn_rd(S[ky][kx].x), fdn_rd(S[ky][kx].y));
+                    S[ky][kx] = cmul(z, w[ky * 5 + kx]);
+                }
+            irfft2_8x8(S, p);
+            const float* a2 = s2 + c * FS_T * FS_T + (py * 8) * FS_T + px * 8;
+#pragma unroll
+            for (int y = 0; y < 8; ++y)
+#pragma unroll
+                for (int x = 0; x < 8; ++x) p[8 * y + x] += a2[y * FS_T + x];
+            store_patch(out + (((size_t)b * C + c0 + c) * H + gy) * W + gx, W, p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 // out = irfft2_8x8( rd(rfft2_8x8(x)) * wspec[c] ) + add.   x, add, out: [B][C][H][W]; wspec: [C][8][5] complex.
@@ -255,4 +355,23 @@ FDN_API int fdn_fdsa_patch_dw(const float* hid, const float* wdw, const float* w
     long long warps = (n + 7) / 8;
     FDN_LAUNCH(k_fdsa_patch_dw, dim3(fdn_cdiv(warps, 4)), dim3(128), 0, st, hid, wdw, wfft, out, vv, E, H, W, n);
     return fdn_check_launch("k_fdsa_patch_dw");
+}
+
+// FDFFN middle section in one kernel: out = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec)   (FDN_arch.py:457-470)
+// h, out [B][C][H][W]; wa, wb [C][9] depthwise 3x3 weights (space.0, space.2); wspec [C][8][5] complex.
+FDN_API int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
+                              cudaStream_t st) {
+    FDN_REQUIRE(h && wa && wb && wspec && out && B > 0 && C > 0, "bad arguments");
+    FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
+    FDN_REQUIRE(fdn_aligned16(out), "out must be 16-byte aligned");
+    const size_t smem = (size_t)FS_C * (FS_HP * FS_HP + FS_SP * FS_SP + FS_T * FS_T) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_fdffn_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    dim3 grid(fdn_cdiv(W, FS_T) * fdn_cdiv(H, FS_T), fdn_cdiv(C, FS_C), B);
+    FDN_LAUNCH(k_fdffn_spatial, grid, dim3(256), smem, st, h, wa, wb, reinterpret_cast<const float2*>(wspec), out, C, H, W);
+    return fdn_check_launch("k_fdffn_spatial");
 }

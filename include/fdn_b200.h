@@ -64,6 +64,11 @@ int fdn_spec_mlp(float* spec, long long plane_stride, long long nbins, int B, in
  * = ffta * exp(-i fftp).  add may be NULL. */
 int fdn_fdffn_patch(const float* x, const float* add, const float* wspec, float* out, int B, int C, int H, int W, cudaStream_t st);
 
+/* FDFFN middle section fused (FDN_arch.py:457-470): out = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec);
+ * wa, wb [C][9] = space.0 / space.2 depthwise weights. */
+int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
+                      cudaStream_t st);
+
 /* FDSA bin algebra (FDN_arch.py:585-632): hid [B][4E][H][W] = (q,k,v,v_value) after to_hidden_dw; wfft [E][8][5];
  * out [B][3E][H][W] = (out1,out2,out3) before norm1..3. */
 int fdn_fdsa_patch(const float* hid, const float* wfft, float* out, int B, int E, int H, int W, cudaStream_t st);

@@ -36,3 +36,8 @@ def test_emu_transformer_block(emu):
 
 def test_emu_fuse(emu):
     P.case_fuse_resample(emu, 32, 8, 8)
+
+
+def test_emu_fdffn_fused_variant(emu, monkeypatch):
+    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
+    P.case_tblock(emu, 32, 8, 16, False, False, seed=21)

@@ -162,3 +162,10 @@ def test_ffma_path_still_matches(cuda_dev, monkeypatch):
     monkeypatch.setenv("FDN_B200_GEMM", "ffma")
     P.case_tblock(cuda_dev, 32, 32, 48, True, True, seed=5)
     P.case_fuse_resample(cuda_dev, 32, 16, 24)
+
+
+def test_fdffn_fused_variant(cuda_dev, monkeypatch):
+    """Opt-in fused FDFFN middle section (dw-GELU-dw + patch FFT + sum in one kernel) against the fp64 oracle."""
+    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
+    P.case_tblock(cuda_dev, 32, 40, 72, False, False, seed=21)      # ragged 32x32 tiles
+    P.case_tblock(cuda_dev, 64, 32, 32, False, False, seed=22)
