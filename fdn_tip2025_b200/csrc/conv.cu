@@ -90,16 +90,23 @@ __global__ void __launch_bounds__(256) k_conv2d(ConvParams q) {
         int co = co0 + o;
         if (co >= q.Cout) continue;
         float bias = q.bias ? q.bias[co] : 0.f;
+        const int oxb = ox0 + tx * 4;
+        float* orow = q.out + (((size_t)b * q.Cout + co) * q.Hout + oy) * q.Wout;
+        if (!q.res && q.head == 0 && (q.Wout & 3) == 0 && oxb + 3 < q.Wout) {      // common case: one 128-bit store
+            *reinterpret_cast<float4*>(orow + oxb) = make_float4(fdn_act(acc[o][0] + bias, q.act), fdn_act(acc[o][1] + bias, q.act),
+                                                                  fdn_act(acc[o][2] + bias, q.act), fdn_act(acc[o][3] + bias, q.act));
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int ox = ox0 + tx * 4 + j;
+            int ox = oxb + j;
             if (ox >= q.Wout) continue;
             float v = acc[o][j] + bias;
             float r = 0.f;
             if (q.res) r = q.res[(((size_t)b * q.Cout + co) * q.Hr + ((size_t)oy << q.res_shift)) * q.Wr + ((size_t)ox << q.res_shift)];
             if (q.head == 1) v = fdn_sigmoid(v + r) + 1e-8f;
             else v = fdn_act(v, q.act) + r;
-            q.out[(((size_t)b * q.Cout + co) * q.Hout + oy) * q.Wout + ox] = v;
+            orow[ox] = v;
         }
     }
 }

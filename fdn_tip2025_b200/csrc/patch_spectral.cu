@@ -168,7 +168,10 @@ __device__ __forceinline__ void dw3_patch(const float* __restrict__ plane, const
     }
 }
 
-__global__ void __launch_bounds__(128) k_fdsa_patch_dw(const float* __restrict__ hid, const float* __restrict__ wdw,
+#ifndef FDSA_MIN_BLOCKS
+#define FDSA_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, FDSA_MIN_BLOCKS) k_fdsa_patch_dw(const float* __restrict__ hid, const float* __restrict__ wdw,
                                                        const float* __restrict__ wfft, float* __restrict__ out, float* __restrict__ vv,
                                                        int E, int H, int W, long long nitems) {
     const int lane = threadIdx.x & 31;
