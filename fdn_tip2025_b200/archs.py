@@ -551,7 +551,7 @@ def _micro_batch(b, h, w):
     env = os.environ.get("FDN_B200_MICRO_BATCH")
     if env:
         return max(1, min(b, int(env)))
-    limit = max(1, min(b, 8, (4 * 1024 * 1024) // (h * w)))
+    limit = max(1, min(b, 8, (8 * 1024 * 1024) // (h * w)))
     while b % limit:          # equal chunks: one CUDA-graph / workspace shape per call
         limit -= 1
     return limit

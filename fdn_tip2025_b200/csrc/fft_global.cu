@@ -241,10 +241,13 @@ __global__ void __launch_bounds__(256) k_rows_r2c(const float* __restrict__ in, 
     const int M = PM.N, Wf = M + 1;
     float2* a = reinterpret_cast<float2*>(smem);
     float2* b = a + rows_per_cta * M;
+    float2* s_tw = b + rows_per_cta * (M + 1);                                          // pass twiddles staged in shared memory
     const int row0 = blockIdx.x * rows_per_cta;
     const int S = min(rows_per_cta, nrows - row0);
     const float2* src = reinterpret_cast<const float2*>(in + (size_t)row0 * 2 * M);      // rows are 8-byte aligned (W even)
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s_tw[i] = PM.tw[i];
     for (int i = threadIdx.x; i < S * M; i += blockDim.x) a[i] = src[i];
+    PM.tw = s_tw;
     __syncthreads();
     float2* res = fft_smem<-1>(PM, a, b, S, M, 1);
     for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
@@ -284,8 +287,11 @@ __global__ void __launch_bounds__(256) k_rows_c2r(RowsC2RParams q, FftPlanDev PM
     const int M = PM.N, Wf = M + 1;
     float2* a = reinterpret_cast<float2*>(smem);
     float2* b = a + q.rows_per_cta * (M + 1);
+    float2* s_tw = b + q.rows_per_cta * (M + 1);
     const int row0 = blockIdx.x * q.rows_per_cta;
     const int S = min(q.rows_per_cta, q.nrows - row0);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) s_tw[i] = PM.tw[i];
+    PM.tw = s_tw;
     // stage the half spectrum (M+1 bins per row) in b, then build Z in a
     for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
         const int r = i / Wf, k = i - r * Wf;
@@ -345,6 +351,9 @@ __global__ void __launch_bounds__(256) k_cols(ColsParams q, FftPlanDev P) {
     const int H = P.N, tc = q.tc;
     float2* a = reinterpret_cast<float2*>(smem);
     float2* b = a + H * tc;
+    float2* s_tw = b + H * tc;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_tw[i] = P.tw[i];
+    P.tw = s_tw;
     const int plane = blockIdx.y;
     const int c0 = blockIdx.x * tc;
     const int nc = min(tc, q.ncols - c0);
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 static int rows_per_cta_for(int W) { return max(1, min(16, 8192 / W)); }              // ~4096 packed complex points per CTA
-static size_t rows_smem(int W, int rpc) { return (size_t)2 * rpc * (W / 2 + 1) * sizeof(float2); }
+static size_t rows_smem(int W, int rpc) { return ((size_t)2 * rpc * (W / 2 + 1) + W / 2) * sizeof(float2); }
 static int cols_per_cta_for(int H) {
     int tc = 8;
     while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;
@@ -597,7 +606,7 @@ FDN_API int fdn_fft_cols(const float* in, long long in_ps, int in_rs, float* out
     q.pha = pha;
     q.w_xa = w_xa;
     q.w_xp = w_xp;
-    size_t smem = (size_t)2 * H * q.tc * sizeof(float2);
+    size_t smem = ((size_t)2 * H * q.tc + H) * sizeof(float2);
     int rc = set_smem(k_cols, smem);
     if (rc) return rc;
     FDN_LAUNCH(k_cols, dim3(fdn_cdiv(ncols, q.tc), planes), dim3(256), smem, st, q, P);
