@@ -151,16 +151,20 @@ __device__ __forceinline__ void butterfly_direct(float2 v[R]) {   // R in {3,5,7
     for (int r = 0; r < R; ++r) v[r] = o[r];
 }
 
+// exact n / d for 0 <= n < 2^22 with rcp = 1.0f / d (one multiply instead of an integer division)
+__device__ __forceinline__ int fast_div(int n, float rcp) { return __float2int_rz(((float)n + 0.5f) * rcp); }
+
 // One radix-R Stockham pass over nseq sequences.  Element n of sequence s lives at s*ss + n*es.
-template <int R, int SGN>
+// COLS = false: sequences are contiguous rows (es == 1): warps stride over sequences, lanes over butterflies.
+// COLS = true : sequences are the nseq = 2^lg interleaved columns of a tile (ss == 1, es == nseq).
+// No integer divisions: j / Ns uses an exact float reciprocal.
+template <int R, int SGN, bool COLS>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
-                                              int Ns, int nseq, int ss, int es) {
+                                              int Ns, int nseq, int ss, int es, int lg) {
     const int N = P.N, NR = N / R, M = N / (Ns * R);
-    const int total = nseq * NR;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int seq, j;
-        if (es == 1) { seq = idx / NR; j = idx - seq * NR; } else { j = idx / nseq; seq = idx - j * nseq; }
-        const int k = j % Ns;
+    const float rcpNs = 1.0f / (float)Ns;
+    auto one = [&](int seq, int j) {
+        const int jh = fast_div(j, rcpNs), k = j - jh * Ns;
         const float2* src = in + seq * ss;
         float2 v[R];
 #pragma unroll
@@ -171,55 +175,78 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         }
         if constexpr (R == 3 || R == 5 || R == 7) butterfly_direct<R, SGN>(v); else butterfly<R, SGN>(v);
         float2* dst = out + seq * ss;
-        const int j0 = (j / Ns) * Ns * R + k;
+        if (!COLS && Ns == 1 && (R % 2 == 0)) {
+            // first pass of a row transform: the R outputs of a butterfly are contiguous -> 128-bit conflict-free stores
+            float4* d4 = reinterpret_cast<float4*>(dst + j * R);
 #pragma unroll
-        for (int r = 0; r < R; ++r) dst[(j0 + r * Ns) * es] = v[r];
+            for (int r = 0; r < R; r += 2) d4[r >> 1] = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
+        } else {
+            const int j0 = jh * Ns * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[(j0 + r * Ns) * es] = v[r];
+        }
+    };
+    if (COLS) {
+        const int total = NR << lg;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) one(idx & (nseq - 1), idx >> lg);
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int seq = warp; seq < nseq; seq += nwarps)
+            for (int j = lane; j < NR; j += 32) one(seq, j);
     }
 }
 
 // Any other prime radix: one thread per output element, direct sum over the R inputs.
-template <int SGN>
+template <int SGN, bool COLS>
 __device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
-                                                      int R, int Ns, int nseq, int ss, int es) {
+                                                      int R, int Ns, int nseq, int ss, int es, int lg) {
     const int N = P.N, NR = N / R, M = N / (Ns * R);
-    const int total = nseq * N;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int seq, o;
-        if (es == 1) { seq = idx / N; o = idx - seq * N; } else { o = idx / nseq; seq = idx - o * nseq; }
-        const int k = o % Ns, r = (o / Ns) % R, jhi = o / (Ns * R);
+    const float rcpNs = 1.0f / (float)Ns, rcpR = 1.0f / (float)R;
+    auto one = [&](int seq, int o) {
+        const int oh = fast_div(o, rcpNs), k = o - oh * Ns;          // o = (jhi*R + r)*Ns + k
+        const int jhi = fast_div(oh, rcpR), r = oh - jhi * R;
         const int j = jhi * Ns + k;
         const int step = (k + r * Ns) * M;     // < N
         const float2* src = in + seq * ss;
         float2 acc = make_float2(0.f, 0.f);
         int t = 0;
-        for (int s = 0; s < R; ++s) {
-            float2 x = src[(j + s * NR) * es];
-            float2 w = P.tw[t];
-            float2 p = tw_mul<SGN>(x, w);
-            acc.x += p.x;
-            acc.y += p.y;
+        for (int q = 0; q < R; ++q) {
+            float2 x = src[(j + q * NR) * es];
+            float2 pr = tw_mul<SGN>(x, P.tw[t]);
+            acc.x += pr.x;
+            acc.y += pr.y;
             t += step;
             if (t >= N) t -= N;
         }
         out[seq * ss + o * es] = acc;
+    };
+    if (COLS) {
+        const int total = N << lg;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) one(idx & (nseq - 1), idx >> lg);
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int seq = warp; seq < nseq; seq += nwarps)
+            for (int o = lane; o < N; o += 32) one(seq, o);
     }
 }
 
 // Full FFT of nseq sequences; ping-pongs between a and b, returns the buffer holding the result.
 // Must be called by all threads of the block; ends with a __syncthreads().
-template <int SGN>
+template <int SGN, bool COLS>
 __device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq, int ss, int es) {
     int Ns = 1;
+    int lg = 0;
+    while ((1 << lg) < nseq) ++lg;           // COLS: nseq is a power of two
     for (int p = 0; p < P.npass; ++p) {
         const int R = P.radix[p];
         switch (R) {
-            case 2: stockham_pass<2, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            case 3: stockham_pass<3, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            case 4: stockham_pass<4, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            case 5: stockham_pass<5, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            case 7: stockham_pass<7, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            case 8: stockham_pass<8, SGN>(a, b, P, Ns, nseq, ss, es); break;
-            default: stockham_pass_generic<SGN>(a, b, P, R, Ns, nseq, ss, es); break;
+            case 2: stockham_pass<2, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 3: stockham_pass<3, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 4: stockham_pass<4, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 5: stockham_pass<5, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 7: stockham_pass<7, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 8: stockham_pass<8, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            default: stockham_pass_generic<SGN, COLS>(a, b, P, R, Ns, nseq, ss, es, lg); break;
         }
         __syncthreads();
         Ns *= R;
@@ -238,29 +265,35 @@ __device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq,
 __global__ void __launch_bounds__(256) k_rows_r2c(const float* __restrict__ in, float2* __restrict__ out, FftPlanDev PM,
                                                   const float2* __restrict__ twW, int nrows, int rows_per_cta) {
     FDN_DYN_SMEM(smem);
-    const int M = PM.N, Wf = M + 1;
+    const int M = PM.N, Wf = M + 1, MS = (M + 1) & ~1;        // even row stride keeps the 128-bit stores of the first pass aligned
     float2* a = reinterpret_cast<float2*>(smem);
-    float2* b = a + rows_per_cta * M;
-    float2* s_tw = b + rows_per_cta * (M + 1);                                          // pass twiddles staged in shared memory
+    float2* b = a + rows_per_cta * MS;
+    float2* s_tw = b + rows_per_cta * MS;                       // pass twiddles staged in shared memory
     const int row0 = blockIdx.x * rows_per_cta;
     const int S = min(rows_per_cta, nrows - row0);
-    const float2* src = reinterpret_cast<const float2*>(in + (size_t)row0 * 2 * M);      // rows are 8-byte aligned (W even)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < M; i += blockDim.x) s_tw[i] = PM.tw[i];
-    for (int i = threadIdx.x; i < S * M; i += blockDim.x) a[i] = src[i];
+    for (int r = warp; r < S; r += nwarps) {
+        const float2* src = reinterpret_cast<const float2*>(in + (size_t)(row0 + r) * 2 * M);   // rows are 8-byte aligned (W even)
+        for (int n = lane; n < M; n += 32) a[r * MS + n] = src[n];
+    }
     PM.tw = s_tw;
     __syncthreads();
-    float2* res = fft_smem<-1>(PM, a, b, S, M, 1);
-    for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
-        const int r = i / Wf, k = i - r * Wf;
-        const float2 zk = res[r * M + (k == M ? 0 : k)];
-        const float2 zc = res[r * M + (k == 0 ? 0 : M - k)];            // conj applied below
-        const float ex = 0.5f * (zk.x + zc.x), ey = 0.5f * (zk.y - zc.y);
-        const float dx = zk.x - zc.x, dy = zk.y + zc.y;                   // D = Z[k] - conj Z[M-k]
-        const float ox = 0.5f * dy, oy = -0.5f * dx;                      // O = -i D / 2
-        const float2 w = twW[k];
-        float2 v = make_float2(ex + (w.x * ox - w.y * oy), ey + (w.x * oy + w.y * ox));
-        if (k == 0 || k == M) v.y = 0.f;                                  // exact for real input
-        out[(size_t)(row0 + r) * Wf + k] = v;
+    float2* res = fft_smem<-1, false>(PM, a, b, S, MS, 1);
+    for (int r = warp; r < S; r += nwarps) {
+        const float2* z = res + r * MS;
+        float2* dst = out + (size_t)(row0 + r) * Wf;
+        for (int k = lane; k < Wf; k += 32) {
+            const float2 zk = z[k == M ? 0 : k];
+            const float2 zc = z[k == 0 ? 0 : M - k];                     // conj applied below
+            const float ex = 0.5f * (zk.x + zc.x), ey = 0.5f * (zk.y - zc.y);
+            const float dx = zk.x - zc.x, dy = zk.y + zc.y;               // D = Z[k] - conj Z[M-k]
+            const float ox = 0.5f * dy, oy = -0.5f * dx;                  // O = -i D / 2
+            const float2 w = twW[k];
+            float2 v = make_float2(ex + (w.x * ox - w.y * oy), ey + (w.x * oy + w.y * ox));
+            if (k == 0 || k == M) v.y = 0.f;                              // exact for real input
+            dst[k] = v;
+        }
     }
 }
 
@@ -284,42 +317,51 @@ struct RowsC2RParams {
 
 __global__ void __launch_bounds__(256) k_rows_c2r(RowsC2RParams q, FftPlanDev PM, const float2* __restrict__ twW) {
     FDN_DYN_SMEM(smem);
-    const int M = PM.N, Wf = M + 1;
+    const int M = PM.N, Wf = M + 1, MS = (M + 1) & ~1;
     float2* a = reinterpret_cast<float2*>(smem);
-    float2* b = a + q.rows_per_cta * (M + 1);
-    float2* s_tw = b + q.rows_per_cta * (M + 1);
+    const int half_elems = (q.rows_per_cta * (M + 1) + 1) & ~1;       // keep both ping-pong buffers 16-byte aligned
+    float2* b = a + half_elems;
+    float2* s_tw = b + half_elems;
     const int row0 = blockIdx.x * q.rows_per_cta;
     const int S = min(q.rows_per_cta, q.nrows - row0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < M; i += blockDim.x) s_tw[i] = PM.tw[i];
     PM.tw = s_tw;
     // stage the half spectrum (M+1 bins per row) in b, then build Z in a
-    for (int i = threadIdx.x; i < S * Wf; i += blockDim.x) {
-        const int r = i / Wf, k = i - r * Wf;
-        float2 v = q.in[(size_t)(row0 + r) * Wf + k];
-        if (k == 0 || k == M) v.y = 0.f;
-        b[r * (M + 1) + k] = v;
+    for (int r = warp; r < S; r += nwarps) {
+        const float2* src = q.in + (size_t)(row0 + r) * Wf;
+        for (int k = lane; k < Wf; k += 32) {
+            float2 v = src[k];
+            if (k == 0 || k == M) v.y = 0.f;
+            b[r * (M + 1) + k] = v;
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < S * M; i += blockDim.x) {
-        const int r = i / M, k = i - r * M;
-        const float2 xk = b[r * (M + 1) + k], xc = b[r * (M + 1) + (M - k)];
-        const float ex = 0.5f * (xk.x + xc.x), ey = 0.5f * (xk.y - xc.y);
-        const float tx = 0.5f * (xk.x - xc.x), ty = 0.5f * (xk.y + xc.y);     // T = (X[k] - conj X[M-k]) / 2
-        const float2 w = twW[k];                                               // O = conj(w) T
-        const float ox = w.x * tx + w.y * ty, oy = w.x * ty - w.y * tx;
-        a[r * M + k] = make_float2(ex - oy, ey + ox);                          // E + i O
+    for (int r = warp; r < S; r += nwarps) {
+        const float2* x = b + r * (M + 1);
+        for (int k = lane; k < M; k += 32) {
+            const float2 xk = x[k], xc = x[M - k];
+            const float ex = 0.5f * (xk.x + xc.x), ey = 0.5f * (xk.y - xc.y);
+            const float tx = 0.5f * (xk.x - xc.x), ty = 0.5f * (xk.y + xc.y);     // T = (X[k] - conj X[M-k]) / 2
+            const float2 w = twW[k];                                               // O = conj(w) T
+            const float ox = w.x * tx + w.y * ty, oy = w.x * ty - w.y * tx;
+            a[r * MS + k] = make_float2(ex - oy, ey + ox);                         // E + i O
+        }
     }
     __syncthreads();
-    float2* res = fft_smem<1>(PM, a, b, S, M, 1);
-    const float nrm = 2.0f * q.norm;                                           // IDFT_M gives (W/2) x
-    float2* dst = reinterpret_cast<float2*>(q.out + (size_t)row0 * 2 * M);
-    const float2* rsrc = q.res ? reinterpret_cast<const float2*>(q.res + (size_t)row0 * 2 * M) : nullptr;
-    for (int i = threadIdx.x; i < S * M; i += blockDim.x) {
-        const int r = i / M;
-        float2 v = make_float2(res[i].x * nrm, res[i].y * nrm);
-        if (rsrc) { const float2 t = rsrc[i]; v.x += q.res_coef * t.x; v.y += q.res_coef * t.y; }
-        if (q.img_scale) { const float sc = q.img_scale[(row0 + r) / q.rows_per_image]; v.x *= sc; v.y *= sc; }
-        dst[i] = v;
+    float2* res = fft_smem<1, false>(PM, a, b, S, MS, 1);
+    const float nrm = 2.0f * q.norm;                                               // IDFT_M gives (W/2) x
+    for (int r = warp; r < S; r += nwarps) {
+        const float2* z = res + r * MS;
+        float2* dst = reinterpret_cast<float2*>(q.out + (size_t)(row0 + r) * 2 * M);
+        const float2* rsrc = q.res ? reinterpret_cast<const float2*>(q.res + (size_t)(row0 + r) * 2 * M) : nullptr;
+        const float sc = q.img_scale ? q.img_scale[(row0 + r) / q.rows_per_image] : 1.0f;
+        for (int n = lane; n < M; n += 32) {
+            float2 v = make_float2(z[n].x * nrm, z[n].y * nrm);
+            if (rsrc) { const float2 t = rsrc[n]; v.x += q.res_coef * t.x; v.y += q.res_coef * t.y; }
+            v.x *= sc; v.y *= sc;
+            dst[n] = v;
+        }
     }
 }
 
@@ -365,9 +407,9 @@ __global__ void __launch_bounds__(256) k_cols(ColsParams q, FftPlanDev P) {
     __syncthreads();
     float2* res;
     if (q.mode == COLS_INV) {
-        res = fft_smem<1>(P, a, b, tc, 1, tc);
+        res = fft_smem<1, true>(P, a, b, tc, 1, tc);
     } else {
-        res = fft_smem<-1>(P, a, b, tc, 1, tc);
+        res = fft_smem<-1, true>(P, a, b, tc, 1, tc);
         float2* other = (res == a) ? b : a;
         // the four self-conjugate bins of a real signal's spectrum are exactly real
         if (q.W > 0) {
@@ -403,7 +445,7 @@ __global__ void __launch_bounds__(256) k_cols(ColsParams q, FftPlanDev P) {
                 }
             }
             __syncthreads();
-            res = fft_smem<1>(P, res, other, tc, 1, tc);
+            res = fft_smem<1, true>(P, res, other, tc, 1, tc);
         }
     }
     if (q.mode == COLS_FWD_ANGLE || q.mode == COLS_FWD_ABS) {
@@ -504,7 +546,7 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 static int rows_per_cta_for(int W) { return max(1, min(16, 8192 / W)); }              // ~4096 packed complex points per CTA
-static size_t rows_smem(int W, int rpc) { return ((size_t)2 * rpc * (W / 2 + 1) + W / 2) * sizeof(float2); }
+static size_t rows_smem(int W, int rpc) { return ((size_t)2 * rpc * (W / 2 + 2) + W / 2) * sizeof(float2); }
 static int cols_per_cta_for(int H) {
     int tc = 8;
     while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;

@@ -62,6 +62,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) {
 #define __fdividef(a, b) ((a) / (b))
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline int __float2int_rz(float x) { return (int)x; }
 static inline float __saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 using std::max;
 using std::min;
