@@ -116,6 +116,16 @@ class _Ctx:
             self.pack[name] = t
         return t
 
+    def packed_grouped(self, key, e):
+        """FDSA project_out weight in the grouped K layout of the gate prologue (packing.grouped_layout)."""
+        name = "mma_grouped:" + key
+        t = self.pack.get(name)
+        if t is None:
+            with torch.no_grad():
+                t = packing.pack_weight(self.sd[key].flatten(1), grouped_e=e)
+            self.pack[name] = t
+        return t
+
     def packed_fuse_out(self, p):
         name = "mma_fuse_out:" + p
         t = self.pack.get(name)
@@ -243,7 +253,7 @@ def _fdsa(cx, x, p):
     else:   # norm1..3, the v_value gate and project_out in one kernel (LayerNorm statistics from a small pre-pass)
         stats = _new(x, b, 3, 2, h * w)
         ops.group_stats(o, stats, 3)
-        ops.pw_mma([o], cx.packed(p + "attn.project_out.weight"), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=e * h * w,
+        ops.pw_mma([o], cx.packed_grouped(p + "attn.project_out.weight", e), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=e * h * w,
                    stats=stats, res=x, res_coef=1.0, passes=1 if mode == "tf32" else 3)
     return out
 

@@ -43,6 +43,7 @@
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
+#define MMA_EB 10            // prologue 2: channels of each LayerNorm group per K block (3 x 10 = 30 of the 32 rows)
 
 struct PwMmaParams {
     const float* src0;      // [B][C0][HW]
@@ -76,6 +77,8 @@ struct PwMmaParams {
     int ncorr;              // 1 when the corrections have their own accumulator
     int nbuf;               // accumulator sets (2 = the epilogue of tile t overlaps the MMAs of tile t+1)
     int bulk;               // 1: one cp.async.bulk per 512-byte channel row (few rows per tile), 0: 16-byte cp.async by 128 threads
+    int E;                  // prologue 2: channels per LayerNorm group (K is then laid out in blocks of 3 x 10 channels)
+    int Kreal;              // number of real input channels (= K except for the grouped layout of prologue 2)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const int ntiles = tiles_per_img * q.B;
     const float* bsrc = q.bpack + (size_t)chunk * nkb * 2 * q.Nc * 32;
     constexpr int panels = PASSES == 3 ? 2 : 1;
-    const int gsize = PRO == 2 ? q.K / 3 : q.K;
+    const int gsize = PRO == 2 ? q.E : q.K;
 
     if (tid == 0) {
         for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
@@ -206,9 +209,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (PRO != 0)
-        for (int i = tid; i < nkb * MMA_KB; i += MMA_THREADS) {
-            s_gam[i] = i < q.K ? q.ln_w[i] : 0.f;
-            s_bet[i] = i < q.K ? q.ln_b[i] : 0.f;
+        for (int i = tid; i < MMA_MAX_K; i += MMA_THREADS) {
+            s_gam[i] = i < q.Kreal ? q.ln_w[i] : 0.f;
+            s_bet[i] = i < q.Kreal ? q.ln_b[i] : 0.f;
         }
     if (q.b_resident) {      // the whole weight chunk stays in shared memory for the lifetime of the CTA
         const float4* src = reinterpret_cast<const float4*>(bsrc);
@@ -254,20 +257,25 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                         const int r = lit % q.ring;
                         if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
                         unsigned char* slot = s_raw + (size_t)r * slot_bytes;
+                        if (PRO == 2) {
+                            // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once
+                            const int ne = min(MMA_EB, q.E - kb * MMA_EB);
+                            if (lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)(4 * ne + (kb == 0 ? 6 : 0)) * len);
+                            __syncwarp();
+                            const int g = lane / MMA_EB, el = lane - g * MMA_EB;
+                            if (lane < 3 * MMA_EB && el < ne)
+                                bulk_g2s(slot + lane * (MMA_TP * 4), q.src0 + ((size_t)b * q.C0 + g * q.E + kb * MMA_EB + el) * HW + p0, len, &raw_full[r]);
+                            if (lane < ne)
+                                bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + lane) * HW + p0, len, &raw_full[r]);
+                        } else {
                         const int rows = min(MMA_KB, q.K - kb * MMA_KB);
-                        if (lane == 0) {
-                            uint32_t bytes = (uint32_t)rows * len * (has_aux ? 2 : 1);
-                            if (PRO == 2 && kb == 0) bytes += 6 * len;
-                            mbar_expect_tx(&raw_full[r], bytes);
-                        }
+                        if (lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)rows * len * (has_aux ? 2 : 1));
                         __syncwarp();
                         if (lane < rows) {
                             const int k = kb * MMA_KB + lane;
                             bulk_g2s(slot + lane * (MMA_TP * 4), src_row(q, b, k) + p0, len, &raw_full[r]);
-                            if (has_aux) {
-                                const int ka = PRO == 2 ? k % gsize : k;
-                                bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0, len, &raw_full[r]);
-                            }
+                            if (has_aux) bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)k * HW + p0, len, &raw_full[r]);
+                        }
                         }
                         if (PRO == 2 && kb == 0 && lane < 6)
                             bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
@@ -282,18 +290,31 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 const int r = lit % q.ring;
                 if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
                 unsigned char* slot = s_raw + (size_t)r * slot_bytes;
+                if (PRO == 2) {
+                    const int ne = min(MMA_EB, q.E - kb * MMA_EB);
+                    for (int i = lt; i < 4 * MMA_EB * 32; i += lthreads) {      // rows 0..29: x (3 groups x 10), rows 30..39: v_value
+                        const int row = i >> 5, ch = i & 31;
+                        const int g = row / MMA_EB, el = row - g * MMA_EB;
+                        if (ch < vch && el < ne) {
+                            if (g < 3)
+                                cp_async16(slot + row * (MMA_TP * 4) + ch * 16,
+                                           q.src0 + ((size_t)b * q.C0 + g * q.E + kb * MMA_EB + el) * HW + p0 + ch * 4);
+                            else
+                                cp_async16(slot + MMA_SLOT_BYTES + el * (MMA_TP * 4) + ch * 16,
+                                           q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + el) * HW + p0 + ch * 4);
+                        }
+                    }
+                } else {
                 const int rows = min(MMA_KB, q.K - kb * MMA_KB);
                 for (int i = lt; i < rows * 32; i += lthreads) {
                     const int row = i >> 5, ch = i & 31;
                     if (ch < vch) {
                         const int k = kb * MMA_KB + row;
                         cp_async16(slot + row * (MMA_TP * 4) + ch * 16, src_row(q, b, k) + p0 + ch * 4);
-                        if (has_aux) {
-                            const int ka = PRO == 2 ? k % gsize : k;
-                            cp_async16(slot + MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16,
-                                       q.aux + (size_t)b * q.aux_bs + (size_t)ka * HW + p0 + ch * 4);
-                        }
+                        if (has_aux)
+                            cp_async16(slot + MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16, q.aux + (size_t)b * q.aux_bs + (size_t)k * HW + p0 + ch * 4);
                     }
+                }
                 }
                 if (PRO == 2 && kb == 0)
                     for (int i = lt; i < 6 * 32; i += lthreads) {
@@ -364,18 +385,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 const int kleft = q.K - kb * MMA_KB;                      // valid channels in this block (may exceed 32)
                 const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
                 if (it >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((it / q.nstage) - 1) & 1);
-                // a 32-channel block touches at most two LayerNorm groups (PRO 2): [0, kbnd) -> g_lo, the rest -> g_lo + 1
-                const int g_lo = PRO == 2 ? (kb * MMA_KB) / gsize : 0;
-                const int kbnd = PRO == 2 ? (g_lo + 1) * gsize - kb * MMA_KB : 0;
-                const float gm_a = g_lo == 0 ? gmu0 : (g_lo == 1 ? gmu1 : gmu2), gr_a = g_lo == 0 ? grs0 : (g_lo == 1 ? grs1 : grs2);
-                const float gm_b = g_lo == 0 ? gmu1 : gmu2, gr_b = g_lo == 0 ? grs1 : grs2;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = half + 2 * i;
                     if (c < nchunks_used) {
                         float hi[4], lo[4];
                         float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
-                        if (PRO != 0) {
+                        if (PRO == 1 || PRO == 3) {
                             g4 = *reinterpret_cast<const float4*>(s_gam + kb * MMA_KB + 4 * c);
                             b4 = *reinterpret_cast<const float4*>(s_bet + kb * MMA_KB + 4 * c);
                         }
@@ -384,16 +400,23 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                         for (int j = 0; j < 4; ++j) {
                             const int kk = 4 * c + j;
                             float x = raw[kk * MMA_TP];
+                            bool ok = pvalid && kk < kleft;
                             if (PRO == 1) {
                                 x = (x - mu) * rs * gj[j] + bj[j];
                             } else if (PRO == 2) {
-                                const float gm = kk < kbnd ? gm_a : gm_b, gr = kk < kbnd ? gr_a : gr_b;
-                                x = ((x - gm) * gr * gj[j] + bj[j]) * raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
+                                // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el
+                                const int g = kk / MMA_EB, el = kk - g * MMA_EB, e = kb * MMA_EB + el;
+                                ok = pvalid && g < 3 && e < q.E;
+                                if (ok) {
+                                    const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
+                                    const int ko = g * q.E + e;
+                                    x = ((x - gm) * gr * s_gam[ko] + s_bet[ko]) * raw[(MMA_SLOT_BYTES / 4) + el * MMA_TP];
+                                }
                             } else if (PRO == 3) {
                                 const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
                                 x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
                             }
-                            if (!pvalid || kk >= kleft) x = 0.f;
+                            if (!ok) x = 0.f;
                             hi[j] = to_tf32(x);
                             lo[j] = to_tf32(x - hi[j]);
                         }
@@ -638,8 +661,15 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     FDN_REQUIRE(fdn_aligned16(bpack) && fdn_aligned16(src0) && (!src1 || fdn_aligned16(src1)), "pointers must be 16-byte aligned");
     PwMmaParams q;
     q.src0 = src0; q.src1 = src1; q.C0 = c0; q.C1 = src1 ? c1 : 0;
-    q.K = q.C0 + q.C1;
-    q.Kpad = (q.K + 7) & ~7;
+    q.Kreal = q.C0 + q.C1;
+    q.E = prologue == 2 ? c0 / 3 : 0;
+    if (prologue == 2) {          // grouped layout: ceil(E/10) blocks of 3 x 10 channels (rows 30, 31 of each block are zero)
+        q.K = ((q.E + MMA_EB - 1) / MMA_EB) * MMA_KB;
+        q.Kpad = q.K;
+    } else {
+        q.K = q.Kreal;
+        q.Kpad = (q.K + 7) & ~7;
+    }
     q.N = N; q.Nc = Nc; q.HW = HW; q.B = B;
     q.bpack = bpack; q.prologue = prologue; q.ln_w = ln_w; q.ln_b = ln_b; q.aux = aux; q.aux_bs = aux_bs; q.stats = stats;
     q.bias = bias; q.film_mul = film_mul; q.film_add = film_add; q.res = res; q.res_coef = res_coef; q.out = out;
@@ -658,13 +688,15 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     const int set_cols = (q.nmain + q.ncorr) * Nc;
     q.nbuf = 2 * set_cols <= 512 ? 2 : 1;
     // copy requests per tile: the TMA unit handles ~1 small bulk request per 64 cycles, so many-row tiles use cp.async instead
-    q.bulk = (q.K * (prologue >= 2 ? 2 : 1) + (prologue == 2 ? 6 : 0)) <= 100 ? 1 : 0;
+    // TMA bulk copies (one per 512-byte channel row) measured equal or faster than 16-byte cp.async for every layer shape once
+    // the gate prologue stopped re-loading v_value three times; cp.async stays selectable with FDN_MMA_BULK=0
+    q.bulk = 1;
     if (const char* e = getenv("FDN_MMA_NBUF")) { if (atoi(e) == 1) { q.nbuf = 1; q.tmem_cols = 32; while (q.tmem_cols < set_cols) q.tmem_cols <<= 1; } }
     if (const char* e = getenv("FDN_MMA_BULK")) q.bulk = atoi(e);
     q.tmem_cols = 32;
     while (q.tmem_cols < q.nbuf * set_cols) q.tmem_cols <<= 1;
     FDN_REQUIRE(q.tmem_cols <= 512, "accumulators do not fit in tensor memory");
-    FDN_REQUIRE(nkb * MMA_KB <= MMA_MAX_K, "too many input channels");
+    FDN_REQUIRE(nkb * MMA_KB <= 1024 && q.Kreal <= MMA_MAX_K, "too many input channels");
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;

@@ -22,9 +22,28 @@ def chunking(n):
     return nc, nchunks
 
 
-def pack_weight(w):
-    """w: [N, K] fp32 -> (bpack flat fp32 tensor, N, Nc, nchunks)."""
+GROUP_BLOCK = 10     # csrc/pw_mma.cu MMA_EB: channels of each LayerNorm group per 32-row K block
+
+
+def grouped_layout(w, e):
+    """FDSA project_out weight [N, 3E] -> [N, nkb*32] in the kernel's grouped K order: block kb holds, for the three
+    LayerNorm groups g, the channels g*E + kb*10 + el (el < 10) at row g*10 + el; rows 30, 31 and missing channels are zero."""
+    n, k = w.shape
+    assert k == 3 * e
+    nkb = (e + GROUP_BLOCK - 1) // GROUP_BLOCK
+    out = torch.zeros(n, nkb * 32, dtype=w.dtype, device=w.device)
+    for kb in range(nkb):
+        ne = min(GROUP_BLOCK, e - kb * GROUP_BLOCK)
+        for g in range(3):
+            out[:, kb * 32 + g * GROUP_BLOCK: kb * 32 + g * GROUP_BLOCK + ne] = w[:, g * e + kb * GROUP_BLOCK: g * e + kb * GROUP_BLOCK + ne]
+    return out
+
+
+def pack_weight(w, grouped_e=None):
+    """w: [N, K] fp32 -> (bpack flat fp32 tensor, N, Nc, nchunks).  grouped_e = E selects the grouped K layout of prologue 2."""
     w = w.detach().float()
+    if grouped_e is not None:
+        w = grouped_layout(w, grouped_e)
     n, k = w.shape
     nc, nchunks = chunking(n)
     kpad = (k + 7) // 8 * 8

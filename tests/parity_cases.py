@@ -328,7 +328,7 @@ def case_pw_mma(dev, k, n, hw=(16, 24), prologue=0, passes=3, two_src=False, see
     bias, res = rnd(n, seed=seed + 3), rnd(b, n, h, w, seed=seed + 4)
     fm, fa = rnd(b, n, h, w, seed=seed + 5), rnd(b, n, h, w, seed=seed + 6)
     xf, wf = x.float().double(), wgt.float().double()
-    packed = packing.pack_weight(dev32(wgt, dev))
+    packed = packing.pack_weight(dev32(wgt, dev), grouped_e=(k // 3 if prologue == 2 else None))
     out = torch.empty(b, n, h, w, device=dev)
     kw = dict(bias=dev32(bias, dev), res=dev32(res, dev), res_coef=1.0, passes=passes)
 

@@ -18,7 +18,7 @@ for name, hw, k, n, pro in shapes:
     h, w = hw // 1120 * 2 if False else 640, hw // 640
     x = torch.randn(B, k, h, w, device=dev)
     wgt = torch.randn(n, k, device=dev) / k ** 0.5
-    packed = packing.pack_weight(wgt)
+    packed = packing.pack_weight(wgt, grouped_e=(k // 3 if pro == 2 else None))
     out = torch.empty(B, n, h, w, device=dev)
     res = torch.randn(B, n, h, w, device=dev)
     kw = {}
