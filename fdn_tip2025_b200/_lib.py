@@ -22,6 +22,7 @@ SIGNATURES = {
     "fdn_fft_cols": "plipliiiiiiipppps",
     "fdn_spec_mlp": "plliips",
     "fdn_fdffn_patch": "ppppiiiis",
+    "fdn_fdffn_patch_dw": "pppppiiiis",
     "fdn_fdffn_spatial": "pppppiiiis",
     "fdn_fdsa_patch": "pppiiiis",
     "fdn_fdsa_patch_dw": "pppppiiiis",

@@ -273,9 +273,10 @@ def _fdffn(cx, x, p):
         s2 = hid
     else:
         ops.dwconv3(hid, cx.flat(p + "ffn.space.0.weight"), s1, mode=1)
-        s2 = _new(x, b, hd, h, w)
-        ops.dwconv3(s1, cx.flat(p + "ffn.space.2.weight"), s2, mode=0)
-        ops.fdffn_patch(hid, s2, cx.ffn_spec(p + "ffn."), s1)      # s1 <- spectral branch + spatial branch
+        t = _new(x, b, hd, h, w)
+        # spectral branch + space.2 evaluated on the patch (one-pixel halo of s1): s2 never goes to HBM
+        ops.fdffn_patch_dw(hid, s1, cx.flat(p + "ffn.space.2.weight"), cx.ffn_spec(p + "ffn."), t)
+        s1, s2 = t, hid
     ops.dwconv3(s1, cx.flat(p + "ffn.dwconv.weight"), s2, mode=2)  # s2 <- gelu(x1) * x2
     out = _new(x, b, c, h, w)
     _conv1x1(cx, [s2], p + "ffn.project_out.weight", out, res=x)

@@ -168,6 +168,64 @@ __device__ __forceinline__ void dw3_patch(const float* __restrict__ plane, const
     }
 }
 
+// p[8*y + x] += depthwise 3x3 of `plane` around the patch (rolling three input rows, zero outside the image)
+__device__ __forceinline__ void dw3_patch_add(const float* __restrict__ plane, const float* __restrict__ w, int H, int W, int y0, int x0,
+                                              float p[64]) {
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = w[i];
+    float r0[10], r1[10], r2[10];
+    load_row10(plane, H, W, y0 - 1, x0, r0);
+    load_row10(plane, H, W, y0, x0, r1);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        load_row10(plane, H, W, y0 + y + 1, x0, r2);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            float a = k[0] * r0[x];
+            a += k[1] * r0[x + 1]; a += k[2] * r0[x + 2];
+            a += k[3] * r1[x]; a += k[4] * r1[x + 1]; a += k[5] * r1[x + 2];
+            a += k[6] * r2[x]; a += k[7] * r2[x + 1]; a += k[8] * r2[x + 2];
+            p[8 * y + x] += a;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { r0[i] = r1[i]; r1[i] = r2[i]; }
+    }
+}
+
+// FDFFN: out = irfft2(rd(rfft2(h)) * wspec[c]) + dw_b(s1)      - the second depthwise conv of the spatial branch
+// (space.2, FDN_arch.py:439-441,457) is evaluated on the patch from s1 with a one-pixel halo, so s2 never exists in HBM.
+__global__ void __launch_bounds__(128) k_fdffn_patch_dw(const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ wb,
+                                                        const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W,
+                                                        long long nitems) {
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nitems) return;
+    const int pw = W >> 3, ph = H >> 3;
+    int px = (int)(item % pw);
+    long long t = item / pw;
+    int py = (int)(t % ph);
+    long long plane = t / ph;              // b*C + c
+    int c = (int)(plane % C);
+    size_t off = (size_t)plane * H * W + (size_t)(py * 8) * W + px * 8;
+    float p[64];
+    {
+        float2 S[8][5];
+        load_patch(h + off, W, p);
+        rfft2_8x8(p, S);
+        const float2* w = wspec + c * 40;
+#pragma unroll
+        for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                float2 z = make_float2(fdn_rd(S[ky][kx].x), fdn_rd(S[ky][kx].y));
+                S[ky][kx] = cmul(z, w[ky * 5 + kx]);
+            }
+        irfft2_8x8(S, p);
+    }
+    dw3_patch_add(s1 + (size_t)plane * H * W, wb + c * 9, H, W, py * 8, px * 8, p);
+    store_patch(out + off, W, p);
+}
+
 #ifndef FDSA_MIN_BLOCKS
 #define FDSA_MIN_BLOCKS 4
 #endif
@@ -377,4 +435,16 @@ FDN_API int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, 
     dim3 grid(fdn_cdiv(W, FS_T) * fdn_cdiv(H, FS_T), fdn_cdiv(C, FS_C), B);
     FDN_LAUNCH(k_fdffn_spatial, grid, dim3(256), smem, st, h, wa, wb, reinterpret_cast<const float2*>(wspec), out, C, H, W);
     return fdn_check_launch("k_fdffn_spatial");
+}
+
+// out = irfft2_8x8(rd(rfft2_8x8(h)) * wspec[c]) + depthwise3x3(s1; wb[c])   (FDFFN spectral branch + space.2, FDN_arch.py:439-441,457-470)
+FDN_API int fdn_fdffn_patch_dw(const float* h, const float* s1, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
+                               cudaStream_t st) {
+    FDN_REQUIRE(h && s1 && wb && wspec && out && B > 0 && C > 0, "bad arguments");
+    FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
+    FDN_REQUIRE(fdn_aligned16(h) && fdn_aligned16(s1) && fdn_aligned16(out), "pointers must be 16-byte aligned");
+    long long n = (long long)B * C * (H / 8) * (W / 8);
+    FDN_LAUNCH_SEQ(k_fdffn_patch_dw, dim3(fdn_cdiv(n, 128)), dim3(128), 0, st, h, s1, wb, reinterpret_cast<const float2*>(wspec), out, C,
+                   H, W, n);
+    return fdn_check_launch("k_fdffn_patch_dw");
 }

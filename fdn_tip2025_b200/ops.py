@@ -75,6 +75,11 @@ def fdffn_patch(x, add, wspec, out):
     _lib.call("fdn_fdffn_patch", _p(x), _p(add), _p(wspec), _p(out), b, c, h, w, _stream())
 
 
+def fdffn_patch_dw(h, s1, wb, wspec, out):
+    b, c, hh, w = h.shape
+    _lib.call("fdn_fdffn_patch_dw", _p(h), _p(s1), _p(wb), _p(wspec), _p(out), b, c, hh, w, _stream())
+
+
 def fdffn_spatial(h, wa, wb, wspec, out):
     b, c, hh, w = h.shape
     _lib.call("fdn_fdffn_spatial", _p(h), _p(wa), _p(wb), _p(wspec), _p(out), b, c, hh, w, _stream())

@@ -64,6 +64,11 @@ int fdn_spec_mlp(float* spec, long long plane_stride, long long nbins, int B, in
  * = ffta * exp(-i fftp).  add may be NULL. */
 int fdn_fdffn_patch(const float* x, const float* add, const float* wspec, float* out, int B, int C, int H, int W, cudaStream_t st);
 
+/* FDFFN spectral branch + the second depthwise conv of the spatial branch (space.2, FDN_arch.py:439-441,457-470):
+ * out = irfft2_8x8(rd(rfft2_8x8(h)) * wspec[c]) + depthwise3x3(s1; wb[c]); s1 = gelu(space.0(h)). */
+int fdn_fdffn_patch_dw(const float* h, const float* s1, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
+                       cudaStream_t st);
+
 /* FDFFN middle section fused (FDN_arch.py:457-470): out = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec);
  * wa, wb [C][9] = space.0 / space.2 depthwise weights. */
 int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
