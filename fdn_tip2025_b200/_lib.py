@@ -37,6 +37,7 @@ SIGNATURES = {
     "fdn_gamma_curve": "pppfls",
     "fdn_fill_border": "ppiiiis",
     "fdn_conv2d": "ppppipiiiiiiiiiis",
+    "fdn_film_maps": "pppppiiiis",
     "fdn_convt4s2": "ppppiiiiiis",
     "fdn_dwconv3": "pppiiiiis",
     "fdn_avgpool3s2": "ppiiis",

@@ -299,8 +299,7 @@ def _fcaffn(cx, x, side, p):
     ops.fft_rows_c2r(spec, y, 1.0 / (h * w))
     del spec
     fmul, fadd = _new(x, b, c, h, w), _new(x, b, c, h, w)
-    ops.conv2d(img, cx.film(p + "ffn2.", "mul"), fmul, pad=1)
-    ops.conv2d(img, cx.film(p + "ffn2.", "add"), fadd, pad=1)
+    ops.film_maps(img, cx.film(p + "ffn2.", "mul"), cx.film(p + "ffn2.", "add"), fmul, fadd)
     t = _new(x, b, c, h, w)
     mode = _gemm_mode()
     if mode == "ffma":

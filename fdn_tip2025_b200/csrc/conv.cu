@@ -179,6 +179,73 @@ FDN_API int fdn_conv2d(const float* in, const float* w, const float* bias, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// FCAFFN FiLM maps (FDN_arch.py:423): mul = conv3_mul(conv1_mul(img)), add = conv3_add(conv1_add(img)), both folded on the
+// host into dense 3->C 3x3 kernels.  One launch produces both maps: a thread keeps the 3x3x6 neighbourhood of its four
+// pixels in registers and loops over 8 output channels (weights broadcast from shared memory).
+// ---------------------------------------------------------------------------------------------------
+#define FILM_CG 8
+__global__ void __launch_bounds__(256) k_film_maps(const float* __restrict__ img, const float* __restrict__ wmul, const float* __restrict__ wadd,
+                                                   float* __restrict__ omul, float* __restrict__ oadd, int C, int H, int W) {
+    __shared__ __align__(16) float sw[2][FILM_CG][28];       // 27 taps (+1 pad) per channel and map
+    const int c0 = blockIdx.y * FILM_CG, b = blockIdx.z;
+    for (int i = threadIdx.x; i < 2 * FILM_CG * 27; i += blockDim.x) {
+        const int m = i / (FILM_CG * 27), r = i - m * FILM_CG * 27, c = r / 27, t = r - c * 27;
+        const float* src = m == 0 ? wmul : wadd;
+        sw[m][c][t] = (c0 + c < C) ? src[(c0 + c) * 27 + t] : 0.f;
+    }
+    __syncthreads();
+    const int W4 = W >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over H * W/4
+    if (i >= (long long)H * W4) return;
+    const int x0 = (int)(i % W4) * 4, y = (int)(i / W4);
+    float nb[3][3][6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = y + dy - 1;
+            if (yy >= 0 && yy < H) {
+                const float* p = img + (((size_t)b * 3 + j) * H + yy) * W + x0;
+                const float4 m = *reinterpret_cast<const float4*>(p);
+                nb[j][dy][0] = x0 > 0 ? p[-1] : 0.f;
+                nb[j][dy][1] = m.x; nb[j][dy][2] = m.y; nb[j][dy][3] = m.z; nb[j][dy][4] = m.w;
+                nb[j][dy][5] = x0 + 4 < W ? p[4] : 0.f;
+            } else {
+#pragma unroll
+                for (int dx = 0; dx < 6; ++dx) nb[j][dy][dx] = 0.f;
+            }
+        }
+    for (int c = 0; c < FILM_CG && c0 + c < C; ++c) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float wv = sw[m][c][(j * 3 + dy) * 3 + dx];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) o[px] += wv * nb[j][dy][px + dx];
+                    }
+            float* dst = (m == 0 ? omul : oadd) + (((size_t)b * C + c0 + c) * H + y) * W + x0;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// mul / add [B][C][H][W] = 3x3 conv (padding 1, no bias) of img [B][3][H][W] with wmul / wadd [C][3][3][3]
+FDN_API int fdn_film_maps(const float* img, const float* wmul, const float* wadd, float* omul, float* oadd, int B, int C, int H, int W,
+                          cudaStream_t st) {
+    FDN_REQUIRE(img && wmul && wadd && omul && oadd && B > 0 && C > 0 && H > 0, "bad arguments");
+    FDN_REQUIRE(W % 4 == 0 && fdn_aligned16(img) && fdn_aligned16(omul) && fdn_aligned16(oadd), "W must be a multiple of 4 and pointers 16-byte aligned");
+    dim3 grid(fdn_cdiv((long long)H * (W / 4), 256), fdn_cdiv(C, FILM_CG), B);
+    FDN_LAUNCH(k_film_maps, grid, dim3(256), 0, st, img, wmul, wadd, omul, oadd, C, H, W);
+    return fdn_check_launch("k_film_maps");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // ConvTranspose2d(k=4, s=2, p=1) + LeakyReLU(0.1): out[2H][2W];  w is [Cin][Cout][4][4]
 // out[oy][ox] += in[iy][ix] * w[ky][kx]  with oy = 2*iy - 1 + ky
 // ---------------------------------------------------------------------------------------------------

@@ -176,6 +176,11 @@ def conv2d(x, w, out, bias=None, res=None, res_shift=0, stride=1, pad=1, act=0, 
               _stream())
 
 
+def film_maps(img, wmul, wadd, omul, oadd):
+    b, c, h, w = omul.shape
+    _lib.call("fdn_film_maps", _p(img), _p(wmul), _p(wadd), _p(omul), _p(oadd), b, c, h, w, _stream())
+
+
 def convt4s2(x, w, bias, out, act=1):
     b, cin, h, wd = x.shape
     _lib.call("fdn_convt4s2", _p(x), _p(w), _p(bias), _p(out), b, cin, w.shape[1], h, wd, act, _stream())

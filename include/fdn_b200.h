@@ -132,6 +132,10 @@ int fdn_fill_border(float* t, const float* value, int planes, int C, int H, int 
  * res is sampled at (y<<res_shift, x<<res_shift) (nearest-downsampled image for the heads). */
 int fdn_conv2d(const float* in, const float* w, const float* bias, const float* res, int res_shift, float* out, int B, int Cin,
                int Hin, int Win, int Cout, int K, int stride, int pad, int act, int head, cudaStream_t st);
+/* FCAFFN FiLM maps (FDN_arch.py:423) in one launch: omul / oadd [B][C][H][W] = 3x3 conv (padding 1) of img [B][3][H][W] with the
+ * folded kernels wmul / wadd [C][3][3][3] = conv3_x.weight * conv1_x.weight. */
+int fdn_film_maps(const float* img, const float* wmul, const float* wadd, float* omul, float* oadd, int B, int C, int H, int W,
+                  cudaStream_t st);
 /* ConvTranspose2d(k=4,s=2,p=1) + activation (FDN_arch.py:21-23,194-195); w [Cin][Cout][4][4] */
 int fdn_convt4s2(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int H, int W, int act,
                  cudaStream_t st);
