@@ -37,10 +37,12 @@ def build(verbose=False, force=False):
     """Compile every CUDA source for sm_100a into one shared library.  Returns the library path."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     stamp = LIB + ".sha256"
-    digest = _digest(_all_inputs(), " ".join(NVCC_FLAGS))
+    digest = _digest(_all_inputs(), " ".join(NVCC_FLAGS) + os.environ.get("FDN_MMA_PROFILE", ""))
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("FDN_MMA_PROFILE") == "1":       # dev build: per-role wait counters in k_pw_mma (tools/mma_wait_profile.py)
+        flags.append("-DFDN_MMA_PROFILE=1")
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

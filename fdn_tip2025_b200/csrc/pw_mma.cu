@@ -28,6 +28,7 @@
 // spread round-robin over up to three main accumulators, which the epilogue adds with IEEE fp32 additions.
 // passes = 1 is single-pass TF32 (reported separately).
 #include "fdn_common.cuh"
+#include <type_traits>
 
 #ifndef FDN_EMU
 
@@ -79,6 +80,7 @@ struct PwMmaParams {
     int bulk;               // 1: one cp.async.bulk per 512-byte channel row (few rows per tile), 0: 16-byte cp.async by 128 threads
     int E;                  // prologue 2: channels per LayerNorm group (K is then laid out in blocks of 3 x 10 channels)
     int Kreal;              // number of real input channels (= K except for the grouped layout of prologue 2)
+    unsigned long long* dbg;  // optional [8] counters: cycles each role spent waiting on each barrier (fdn_pw_mma_set_debug)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,17 +94,35 @@ __device__ __forceinline__ float to_tf32(float x) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Wait for the phase with the given parity.  A failed probe backs off with nanosleep so that polling warps do not steal
+// issue slots from the role that is the bottleneck (measured with fdn_pw_mma_set_debug: idle roles were spinning 40-60 %).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    while (!done) {
+        asm volatile("nanosleep.u32 40;" ::: "memory");
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// mbar_wait that charges the waiting time to a debug counter (only one thread per role records)
+#ifndef FDN_MMA_PROFILE
+#define FDN_MMA_PROFILE 0      // 1: per-role wait counters (fdn_pw_mma_set_debug); costs registers, so off in the product build
+#endif
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long* acc, bool rec) {
+    if (!FDN_MMA_PROFILE || !rec) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -162,6 +182,43 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ const float* src_row(const PwMmaParams& q, int b, int k) {
     if (k < q.C0) return q.src0 + ((size_t)b * q.C0 + k) * q.HW;
     return q.src1 + ((size_t)b * q.C1 + (k - q.C0)) * q.HW;
+}
+
+// Epilogue of one 16-column group of one pixel (thread): planes are HW floats apart.  All loads are issued before the first
+// store (out may alias res for in-place residuals); null pointers switch a stage off in the generic instantiation, offsets stay 32-bit (16 planes * HW * 4 B < 2^31 for any image we accept).
+template <bool FULL, bool RES, bool FILM, bool BIAS>
+__device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const float* rp, const float* fm, const float* fa,
+                                          const float* bias, const float (&rpre)[16], bool pre, float res_coef, int HW, int nvalid) {
+    if (BIAS && bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (FULL || j < nvalid) acc[j] += bias[j];
+    }
+    if (FILM && fm != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (FULL || j < nvalid) acc[j] = acc[j] * fm[j * HW] + fa[j * HW];
+    }
+    if (RES) {
+        if (pre) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += res_coef * rpre[j];
+        } else if (rp != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 16; h += 8) {         // two batches of eight loads: enough memory parallelism, half the registers
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (FULL || h + j < nvalid) r[j] = rp[(h + j) * HW];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (FULL || h + j < nvalid) acc[h + j] += res_coef * r[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (FULL || j < nvalid) op[j * HW] = acc[j];
 }
 
 template <int PRO, int PASSES>
@@ -226,6 +283,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const int nmain = q.nmain;
+    unsigned long long w0 = 0, w1 = 0;            // debug: cycles spent waiting (recorded by one thread per role)
+    const bool rec = FDN_MMA_PROFILE && q.dbg != nullptr && (tid == 0 || tid == MMA_EPI_WARP0 * 32 || tid == MMA_MMA_WARP * 32 || tid == MMA_LOAD_WARP0 * 32);
+    const long long t_start = FDN_MMA_PROFILE ? clock64() : 0;
 
     if (warp >= MMA_LOAD_WARP0) {
         // =============================================== loaders ====================================================
@@ -255,7 +315,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;
                     for (int kb = 0; kb < nkb; ++kb, ++lit) {
                         const int r = lit % q.ring;
-                        if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
+                        if (lit >= (uint32_t)q.ring) mbar_wait_t(&raw_empty[r], ((lit / q.ring) - 1) & 1, &w0, rec);
                         unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                         if (PRO == 2) {
                             // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once
@@ -343,7 +403,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 // LayerNorm statistics over all K channels of this pixel, from the raw ring (all K blocks of the tile)
                 float s = 0.f;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1);
+                    mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
                     const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
                     const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
 #pragma unroll
@@ -374,7 +434,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int r = it % q.ring;
                 const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
-                mbar_wait(&raw_full[r], (it / q.ring) & 1);
+                mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
                 if (PRO == 2 && kb == 0) {
                     const float* st = raw + 2 * (MMA_SLOT_BYTES / 4);
                     gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
@@ -384,46 +444,58 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 unsigned char* stage = s_stage + s * stage_bytes;
                 const int kleft = q.K - kb * MMA_KB;                      // valid channels in this block (may exceed 32)
                 const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
-                if (it >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((it / q.nstage) - 1) & 1);
+                if (it >= (uint32_t)q.nstage) mbar_wait_t(&a_empty[s], ((it / q.nstage) - 1) & 1, &w1, rec);
+                // The conversion is specialised on this thread's half (0/1) so that every per-element index (channel, LayerNorm
+                // group, v_value row, smem offsets) is a compile-time constant: ~3x fewer instructions than runtime indexing.
+                auto convert = [&](auto half_c) {
+                    constexpr int HALF = decltype(half_c)::value;
+                    const float* gam_kb = s_gam + kb * MMA_KB;
+                    const float* bet_kb = s_bet + kb * MMA_KB;
+                    const int e0 = kb * MMA_EB;                     // prologue 2: first channel (within a group) of this block
+                    const float* gam_g = s_gam + e0;
+                    const float* bet_g = s_bet + e0;
+                    const int E = q.E;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = half + 2 * i;
-                    if (c < nchunks_used) {
-                        float hi[4], lo[4];
-                        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
-                        if (PRO == 1 || PRO == 3) {
-                            g4 = *reinterpret_cast<const float4*>(s_gam + kb * MMA_KB + 4 * c);
-                            b4 = *reinterpret_cast<const float4*>(s_bet + kb * MMA_KB + 4 * c);
-                        }
-                        const float gj[4] = {g4.x, g4.y, g4.z, g4.w}, bj[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int kk = 4 * c + j;
-                            float x = raw[kk * MMA_TP];
-                            bool ok = pvalid && kk < kleft;
-                            if (PRO == 1) {
-                                x = (x - mu) * rs * gj[j] + bj[j];
-                            } else if (PRO == 2) {
-                                // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el
-                                const int g = kk / MMA_EB, el = kk - g * MMA_EB, e = kb * MMA_EB + el;
-                                ok = pvalid && g < 3 && e < q.E;
-                                if (ok) {
-                                    const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
-                                    const int ko = g * q.E + e;
-                                    x = ((x - gm) * gr * s_gam[ko] + s_bet[ko]) * raw[(MMA_SLOT_BYTES / 4) + el * MMA_TP];
-                                }
-                            } else if (PRO == 3) {
-                                const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
-                                x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = HALF + 2 * i;
+                        if (c < nchunks_used) {
+                            float hi[4], lo[4];
+                            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+                            if (PRO == 1 || PRO == 3) {
+                                g4 = *reinterpret_cast<const float4*>(gam_kb + 4 * c);
+                                b4 = *reinterpret_cast<const float4*>(bet_kb + 4 * c);
                             }
-                            if (!ok) x = 0.f;
-                            hi[j] = to_tf32(x);
-                            lo[j] = to_tf32(x - hi[j]);
+                            const float gj[4] = {g4.x, g4.y, g4.z, g4.w}, bj[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int kk = 4 * c + j;
+                                float x = raw[kk * MMA_TP];
+                                bool ok = pvalid && kk < kleft;
+                                if (PRO == 1) {
+                                    x = (x - mu) * rs * gj[j] + bj[j];
+                                } else if (PRO == 2) {
+                                    // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el
+                                    const int g = kk / MMA_EB, el = kk - g * MMA_EB;
+                                    ok = pvalid && g < 3 && e0 + el < E;
+                                    if (g < 3) {
+                                        const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
+                                        // gamma/beta reads past E stay inside the (zero padded) table and are discarded by ok
+                                        x = ((x - gm) * gr * gam_g[g * E + el] + bet_g[g * E + el]) * raw[(MMA_SLOT_BYTES / 4) + el * MMA_TP];
+                                    }
+                                } else if (PRO == 3) {
+                                    const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
+                                    x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
+                                }
+                                if (!ok) x = 0.f;
+                                hi[j] = to_tf32(x);
+                                lo[j] = to_tf32(x - hi[j]);
+                            }
+                            *reinterpret_cast<float4*>(stage + soff[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            if (PASSES == 3) *reinterpret_cast<float4*>(stage + a_bytes + soff[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                         }
-                        *reinterpret_cast<float4*>(stage + soff[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        if (PASSES == 3) *reinterpret_cast<float4*>(stage + a_bytes + soff[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                }
+                };
+                if (half == 0) convert(std::integral_constant<int, 0>{}); else convert(std::integral_constant<int, 1>{});
                 mbar_arrive(&raw_empty[r]);            // this thread is done with the raw slot
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&a_full[s]);
@@ -436,12 +508,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
             const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
             const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;          // how often this accumulator set was used before
-            if (use >= 1) mbar_wait(&acc_empty[buf], (use - 1) & 1);           // the epilogue has drained this accumulator set
+            if (use >= 1) mbar_wait_t(&acc_empty[buf], (use - 1) & 1, &w1, rec);  // the epilogue has drained this accumulator set
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             bool corr_started = false;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % q.nstage;
-                mbar_wait(&a_full[s], (it / q.nstage) & 1);
+                mbar_wait_t(&a_full[s], (it / q.nstage) & 1, &w0, rec);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t a_hi = smem_u32(s_stage + s * stage_bytes), a_lo = a_hi + a_bytes;
@@ -476,10 +548,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         const int c16_begin = col_half == 0 ? 0 : c16_mid, c16_end = col_half == 0 ? c16_mid : ncol16;
         const bool has_res = q.res != nullptr, has_film = q.film_mul != nullptr, has_bias = q.bias != nullptr;
         const float res_coef = q.res_coef;
+        const int epi_mode = (has_film || has_bias) ? 2 : (has_res ? 1 : 0);
+        float* const out_p = q.out;
+        const float* const res_p = q.res;
+        const int N_all = q.N;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t titer = 0;
         const uint32_t set_cols = (uint32_t)((nmain + q.ncorr) * q.Nc);
-        // residual of this warp's first 16-column group, fetched one tile ahead so its HBM latency is hidden behind a tile
+        // residual of this warp's first 16-column group, fetched one tile ahead (right after the previous tile consumed it) so its
+        // HBM latency is hidden behind a tile
         float rnext[16];
         auto prefetch_res = [&](int tile_n) {
             const int bn = tile_n / tiles_per_img, pn = (tile_n - bn * tiles_per_img) * MMA_TP + row;
@@ -497,11 +574,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
             const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;
             const uint32_t tacc = tlane + buf * set_cols;
-            float rpre[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) rpre[j] = rnext[j];
-            prefetch_res(tile + gridDim.x);
-            mbar_wait(&acc_full[buf], use & 1);
+            mbar_wait_t(&acc_full[buf], use & 1, &w0, rec);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int c16 = c16_begin; c16 < c16_end; ++c16) {
                 float acc[16];
@@ -525,39 +598,37 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 }
                 const int n0 = chunk * q.Nc + c16 * 16;
                 if (valid) {
-                    float* op = q.out + base + (size_t)(c16 * 16) * HW;
-                    if (has_bias) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += (n0 + j < q.N) ? q.bias[n0 + j] : 0.f;
+                    const size_t goff = base + (size_t)(c16 * 16) * HW;
+                    const int nvalid = N_all - n0;            // >= 16: whole group, no per-column predicate
+                    const bool pre = c16 == c16_begin;
+                    if (epi_mode == 0) {
+                        if (nvalid >= 16) epi_group<true, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HW, 16);
+                        else epi_group<false, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HW, nvalid);
+                    } else if (epi_mode == 1) {
+                        if (nvalid >= 16) epi_group<true, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HW, 16);
+                        else epi_group<false, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HW, nvalid);
+                    } else {
+                        const float* bn = has_bias ? q.bias + n0 : nullptr;
+                        const float* fm = has_film ? q.film_mul + goff : nullptr;
+                        const float* fa = has_film ? q.film_add + goff : nullptr;
+                        // generic: null-guarded (rpre is zero when there is no residual)
+                        epi_group<false, true, true, true>(acc, out_p + goff, has_res ? res_p + goff : nullptr, fm, fa, bn, rnext, pre, res_coef, HW, min(nvalid, 16));
                     }
-                    if (has_film) {
-                        const float* fm = q.film_mul + base + (size_t)(c16 * 16) * HW;
-                        const float* fa = q.film_add + base + (size_t)(c16 * 16) * HW;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < q.N) acc[j] = acc[j] * fm[(size_t)j * HW] + fa[(size_t)j * HW];
-                    }
-                    if (has_res) {
-                        if (c16 == c16_begin) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) acc[j] += res_coef * rpre[j];
-                        } else {
-                            const float* rp = q.res + base + (size_t)(c16 * 16) * HW;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (n0 + j < q.N) acc[j] += res_coef * rp[(size_t)j * HW];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + j < q.N) op[(size_t)j * HW] = acc[j];
                 }
+                // the prefetched residual has been consumed: refill the same registers for the next tile of this CTA
+                if (c16 == c16_begin) prefetch_res(tile + gridDim.x);
             }
             if (c16_begin >= c16_end) {          // a warp without columns (Nc == 16) still takes part in the hand-back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&acc_empty[buf]);
             }
         }
+    }
+    if (FDN_MMA_PROFILE && rec) {     // [0,1] producer (raw_full, a_empty) [2] epilogue (acc_full) [3,4] MMA (a_full, acc_empty) [5] loader (raw_empty) [6] total
+        const int role = tid == 0 ? 0 : (tid == MMA_EPI_WARP0 * 32 ? 2 : (tid == MMA_MMA_WARP * 32 ? 3 : 5));
+        atomicAdd(&q.dbg[role], w0);
+        if (role == 0 || role == 3) atomicAdd(&q.dbg[role + 1], w1);
+        if (role == 0) atomicAdd(&q.dbg[6], (unsigned long long)(clock64() - t_start));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -615,6 +686,15 @@ static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
     return found;
 }
 #endif  // !FDN_EMU
+
+static unsigned long long* g_pw_mma_dbg = nullptr;
+// Development aid: device buffer of 8 uint64 counters that every following fdn_pw_mma launch adds its per-role wait cycles to
+// (NULL disables).  [0] producers on raw_full, [1] producers on a_empty, [2] epilogue on acc_full, [3] MMA on a_full,
+// [4] MMA on acc_empty, [5] loader on raw_empty, [6] total cycles (summed over CTAs).
+FDN_API int fdn_pw_mma_set_debug(void* counters) {
+    g_pw_mma_dbg = reinterpret_cast<unsigned long long*>(counters);
+    return 0;
+}
 
 FDN_API int fdn_has_tcgen05() {
 #ifdef FDN_EMU
@@ -674,6 +754,7 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     q.bpack = bpack; q.prologue = prologue; q.ln_w = ln_w; q.ln_b = ln_b; q.aux = aux; q.aux_bs = aux_bs; q.stats = stats;
     q.bias = bias; q.film_mul = film_mul; q.film_add = film_add; q.res = res; q.res_coef = res_coef; q.out = out;
     q.passes = passes;
+    q.dbg = g_pw_mma_dbg;
     // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
     q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;

@@ -102,6 +102,9 @@ int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1, int c1
  * (statistics from fdn_group_stats) times v_value=aux (FDN_arch.py:633-639), 3 FCAFFN mix LN(src)*aux + aux (FDN_arch.py:420).  Epilogue: +bias,
  * *film_mul+film_add, +res_coef*res.  passes: 3 = 3xTF32 split (fp32-level accuracy), 1 = single TF32. */
 int fdn_has_tcgen05(void);
+/* Development aid: 8 uint64 device counters receiving the per-role barrier wait cycles of following fdn_pw_mma launches (NULL = off).
+ * Counting is compiled in only with -DFDN_MMA_PROFILE=1 (FDN_MMA_PROFILE=1 python -m fdn_tip2025_b200.build); otherwise a no-op. */
+int fdn_pw_mma_set_debug(void* counters);
 int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, const float* bpack, int N, int Nc, int nchunks, int prologue,
                const float* ln_w, const float* ln_b, const float* aux, long long aux_bs, const float* stats, const float* bias,
                const float* film_mul, const float* film_add, const float* res, float res_coef, float* out, int B, int HW, int passes,
