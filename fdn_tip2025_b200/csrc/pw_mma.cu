@@ -6,12 +6,13 @@
 // FDSA to_hidden / project_out, FDFFN project_in / project_out, FCAFFN project_in / project_out, Fuse conv / conv2
 // (FDN_arch.py:388-389, 451-452, 562, 566, 685-686).
 //
-// Persistent, warp-specialised kernel (20 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
-//   warps 17-19 loaders: stream raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
-//               into a shared-memory ring with 16-byte cp.async copies whose completion arrives on the slot's mbarrier
-//               (cp.async.mbarrier.arrive) - several tiles ahead of the consumers, which keeps enough bytes in flight to
-//               cover HBM latency.  (One cp.async.bulk per 512-byte channel row was measured to be request-rate bound
-//               in the TMA unit for K > 64.)
+// Persistent, warp-specialised kernel (19 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
+//   warps 17-18 loaders: stream raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
+//               into a shared-memory ring, one TMA bulk copy (cp.async.bulk, 512 contiguous bytes) per channel row with
+//               completion counted on the slot's mbarrier - several K blocks ahead of the consumers, which keeps enough
+//               bytes in flight to cover HBM latency.  Issuing a bulk copy costs ~60 cycles of the issuing thread, so the
+//               rows are interleaved over the lanes of both warps.  When the weights do not fit in shared memory the last
+//               loader warp streams one weight panel per K block instead.  (FDN_MMA_BULK=0 selects 16-byte cp.async.)
 //   warps 0-7   producers: two threads per pixel; take the LayerNorm statistics from shared memory (two-pass mean /
 //               biased variance like the reference), apply the per-pixel prologue, split each value into tf32 hi + lo
 //               and store it into the canonical K-major SWIZZLE_128B operand stage
@@ -25,7 +26,8 @@
 // Precision: passes = 3 ("3xTF32", default) splits both operands into tf32 hi + tf32 lo and accumulates
 // hi*hi + hi*lo + lo*hi.  The split itself is exact to 7e-8; because the tensor core truncates its fp32 accumulator after
 // every instruction, the large hi*hi sum and the small corrections live in separate TMEM accumulators and long K is
-// spread round-robin over up to three main accumulators, which the epilogue adds with IEEE fp32 additions.
+// spread round-robin over up to three main accumulators, which the epilogue adds with IEEE fp32 additions.  For Nc <= 128
+// A_hi x [B_hi;B_lo] is issued as one MMA of N = 2*Nc into an adjacent (main, correction) accumulator pair.
 // passes = 1 is single-pass TF32 (reported separately).
 #include "fdn_common.cuh"
 #include <type_traits>
@@ -38,12 +40,16 @@
 #define MMA_EPI_WARP0 8
 #define MMA_EPI_THREADS 256
 #define MMA_MMA_WARP 16
-#define MMA_LOAD_WARP0 17     // three loader warps
-#define MMA_LOAD_THREADS 96
-#define MMA_THREADS 640
+#define MMA_LOAD_WARP0 17     // two loader warps (19 warps -> 104 registers per thread; a third loader warp caps them at 96 and spills)
+#define MMA_LOAD_THREADS 64
+#define MMA_THREADS 608
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
+// prologue 2 packs its ring slot: 30 gate rows, 10 v_value rows, 6 statistics rows (23 KB instead of 35 KB -> deeper ring)
+#define MMA_P2_V_OFF (3 * MMA_EB * MMA_TP * 4)
+#define MMA_P2_ST_OFF (4 * MMA_EB * MMA_TP * 4)
+#define MMA_P2_SLOT ((4 * MMA_EB + 6) * MMA_TP * 4)
 #define MMA_EB 10            // prologue 2: channels of each LayerNorm group per K block (3 x 10 = 30 of the 32 rows)
 
 struct PwMmaParams {
@@ -74,6 +80,9 @@ struct PwMmaParams {
     int nstage;             // operand stages (1 or 2)
     int ring;               // raw ring slots
     int nmain;              // main accumulators (K blocks round-robin)
+    int merge;              // 1: A_hi x [B_hi;B_lo] is one MMA of N = 2*Nc into a (main, correction) accumulator pair
+    int set_cols;           // TMEM columns of one accumulator set
+    uint32_t idesc2;        // instruction descriptor with N = 2*Nc (merge)
     int tmem_cols;          // power of two >= nbuf * (nmain + ncorr) * Nc
     int ncorr;              // 1 when the corrections have their own accumulator
     int nbuf;               // accumulator sets (2 = the epilogue of tile t overlaps the MMAs of tile t+1)
@@ -224,10 +233,11 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
 template <int PRO, int PASSES>
 __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // align by pointer arithmetic on the shared array (an integer round trip would turn every access into a generic LD/ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr uint32_t a_bytes = MMA_TP * 128;
     constexpr bool has_aux = PRO >= 2;
-    constexpr uint32_t slot_bytes = MMA_SLOT_BYTES * (has_aux ? 2 : 1) + (PRO == 2 ? 6 * MMA_TP * 4 : 0);
+    constexpr uint32_t slot_bytes = PRO == 2 ? MMA_P2_SLOT : MMA_SLOT_BYTES * (has_aux ? 2 : 1);
     const uint32_t b_bytes = (uint32_t)q.Nc * 128;
     const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
     const uint32_t bres_bytes = q.b_resident ? (uint32_t)nkb * 2 * b_bytes : 0;
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         // raw_full[r] is deferred by the hardware until its copies have landed
         const int lt = tid - MMA_LOAD_WARP0 * 32;
         uint32_t lit = 0;
-        if (!q.b_resident && warp == MMA_LOAD_WARP0 + 2) {
+        if (!q.b_resident && warp == MMA_LOAD_WARP0 + MMA_LOAD_THREADS / 32 - 1) {
             // weight panels that do not fit in shared memory: one contiguous TMA bulk copy per K block straight into the
             // operand stage (the packed image is contiguous in global memory); completion counts on a_full[s]
             if (lane == 0) {
@@ -308,8 +318,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     }
             }
         } else if (q.bulk) {
-            // few channel rows per tile: one TMA bulk copy (512 contiguous bytes) per row, issued by the lanes of one warp
-            if (warp == MMA_LOAD_WARP0)
+            // one TMA bulk copy (512 contiguous bytes) per channel row.  Issuing a bulk copy costs ~60 cycles of one thread's
+            // uniform datapath, so the rows of every K block are interleaved over all loader warps that do not stream weights.
+            const int nlw = q.b_resident ? MMA_LOAD_THREADS / 32 : MMA_LOAD_THREADS / 32 - 1;
+            const int lw = warp - MMA_LOAD_WARP0;
+            if (lw < nlw)
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                     const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
                     const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;
@@ -318,27 +331,35 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                         if (lit >= (uint32_t)q.ring) mbar_wait_t(&raw_empty[r], ((lit / q.ring) - 1) & 1, &w0, rec);
                         unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                         if (PRO == 2) {
-                            // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once
+                            // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once;
+                            // virtual rows 0..29 x, 30..39 v_value, 40..45 the LayerNorm statistics (first K block only)
                             const int ne = min(MMA_EB, q.E - kb * MMA_EB);
-                            if (lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)(4 * ne + (kb == 0 ? 6 : 0)) * len);
-                            __syncwarp();
-                            const int g = lane / MMA_EB, el = lane - g * MMA_EB;
-                            if (lane < 3 * MMA_EB && el < ne)
-                                bulk_g2s(slot + lane * (MMA_TP * 4), q.src0 + ((size_t)b * q.C0 + g * q.E + kb * MMA_EB + el) * HW + p0, len, &raw_full[r]);
-                            if (lane < ne)
-                                bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + lane) * HW + p0, len, &raw_full[r]);
+                            if (lw == 0 && lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)(4 * ne + (kb == 0 ? 6 : 0)) * len);
+                            for (int vi = lane * nlw + lw; vi < 4 * MMA_EB + 6; vi += 32 * nlw) {      // virtual rows of this lane
+                                const int g = vi / MMA_EB, el = vi - g * MMA_EB;
+                                if (g < 3) {
+                                    if (el < ne)
+                                        bulk_g2s(slot + vi * (MMA_TP * 4), q.src0 + ((size_t)b * q.C0 + g * q.E + kb * MMA_EB + el) * HW + p0, len, &raw_full[r]);
+                                } else if (g == 3) {
+                                    if (el < ne)
+                                        bulk_g2s(slot + MMA_P2_V_OFF + el * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + el) * HW + p0, len, &raw_full[r]);
+                                } else if (kb == 0) {
+                                    const int sr = vi - 4 * MMA_EB;
+                                    bulk_g2s(slot + MMA_P2_ST_OFF + sr * (MMA_TP * 4), q.stats + ((size_t)b * 6 + sr) * HW + p0, len, &raw_full[r]);
+                                }
+                            }
                         } else {
-                        const int rows = min(MMA_KB, q.K - kb * MMA_KB);
-                        if (lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)rows * len * (has_aux ? 2 : 1));
-                        __syncwarp();
-                        if (lane < rows) {
-                            const int k = kb * MMA_KB + lane;
-                            bulk_g2s(slot + lane * (MMA_TP * 4), src_row(q, b, k) + p0, len, &raw_full[r]);
-                            if (has_aux) bulk_g2s(slot + MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)k * HW + p0, len, &raw_full[r]);
+                            const int rows = min(MMA_KB, q.K - kb * MMA_KB);
+                            if (lw == 0 && lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)rows * len * (has_aux ? 2 : 1));
+                            for (int vi = lane * nlw + lw; vi < (has_aux ? 2 : 1) * rows; vi += 32 * nlw) {
+                                if (vi < rows) {
+                                    bulk_g2s(slot + vi * (MMA_TP * 4), src_row(q, b, kb * MMA_KB + vi) + p0, len, &raw_full[r]);
+                                } else {
+                                    const int ar = vi - rows;
+                                    bulk_g2s(slot + MMA_SLOT_BYTES + ar * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_KB + ar) * HW + p0, len, &raw_full[r]);
+                                }
+                            }
                         }
-                        }
-                        if (PRO == 2 && kb == 0 && lane < 6)
-                            bulk_g2s(slot + 2 * MMA_SLOT_BYTES + lane * (MMA_TP * 4), q.stats + ((size_t)b * 6 + lane) * HW + p0, len, &raw_full[r]);
                     }
                 }
         } else {
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                                 cp_async16(slot + row * (MMA_TP * 4) + ch * 16,
                                            q.src0 + ((size_t)b * q.C0 + g * q.E + kb * MMA_EB + el) * HW + p0 + ch * 4);
                             else
-                                cp_async16(slot + MMA_SLOT_BYTES + el * (MMA_TP * 4) + ch * 16,
+                                cp_async16(slot + MMA_P2_V_OFF + el * (MMA_TP * 4) + ch * 16,
                                            q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + el) * HW + p0 + ch * 4);
                         }
                     }
@@ -380,7 +401,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     for (int i = lt; i < 6 * 32; i += lthreads) {
                         const int row = i >> 5, ch = i & 31;
                         if (ch < vch)
-                            cp_async16(slot + 2 * MMA_SLOT_BYTES + row * (MMA_TP * 4) + ch * 16, q.stats + ((size_t)b * 6 + row) * HW + p0 + ch * 4);
+                            cp_async16(slot + MMA_P2_ST_OFF + row * (MMA_TP * 4) + ch * 16, q.stats + ((size_t)b * 6 + row) * HW + p0 + ch * 4);
                     }
                 cp_async_arrive(&raw_full[r]);
             }
@@ -436,7 +457,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
                 mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
                 if (PRO == 2 && kb == 0) {
-                    const float* st = raw + 2 * (MMA_SLOT_BYTES / 4);
+                    const float* st = raw + MMA_P2_ST_OFF / 4;
                     gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
                     gmu2 = st[4 * MMA_TP]; grs2 = st[5 * MMA_TP];
                 }
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                                     if (g < 3) {
                                         const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
                                         // gamma/beta reads past E stay inside the (zero padded) table and are discarded by ok
-                                        x = ((x - gm) * gr * gam_g[g * E + el] + bet_g[g * E + el]) * raw[(MMA_SLOT_BYTES / 4) + el * MMA_TP];
+                                        x = ((x - gm) * gr * gam_g[g * E + el] + bet_g[g * E + el]) * raw[MMA_P2_V_OFF / 4 + el * MMA_TP];
                                     }
                                 } else if (PRO == 3) {
                                     const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
@@ -504,7 +525,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     } else if (warp == MMA_MMA_WARP) {
         // =============================================== MMA issuer ================================================
         uint32_t it = 0, titer = 0;
-        const uint32_t set_cols = (uint32_t)((nmain + q.ncorr) * q.Nc);
+        const uint32_t set_cols = (uint32_t)q.set_cols;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
             const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
             const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;          // how often this accumulator set was used before
@@ -522,6 +543,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     const int ksteps = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 3;
                     const uint32_t d_main = tmem_base + buf * set_cols + (uint32_t)((kb % nmain) * q.Nc);
                     const uint32_t d_corr = q.ncorr ? tmem_base + buf * set_cols + (uint32_t)(nmain * q.Nc) : d_main;
+                    if (PASSES == 3 && q.merge) {
+                        // pair (main, correction) in adjacent TMEM columns: [B_hi;B_lo] are adjacent panels, so A_hi x both is one
+                        // MMA of N = 2*Nc (a third fewer instructions and A_hi is read from shared memory once)
+                        const uint32_t d_pair = tmem_base + buf * set_cols + (uint32_t)((kb % nmain) * 2 * q.Nc);
+                        for (int t = 0; t < ksteps; ++t) {
+                            const uint32_t koff = (uint32_t)t * 32;
+                            umma_tf32(d_pair, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc2, (kb >= nmain || t > 0) ? 1u : 0u);
+                            umma_tf32(d_pair + (uint32_t)q.Nc, make_desc(a_lo + koff), make_desc(b_hi + koff), q.idesc, 1u);
+                        }
+                    } else
                     for (int t = 0; t < ksteps; ++t) {
                         const uint32_t koff = (uint32_t)t * 32;       // 8 tf32 = 32 bytes along K inside the swizzle atom
                         umma_tf32(d_main, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc, (kb >= nmain || t > 0) ? 1u : 0u);
@@ -554,7 +585,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         const int N_all = q.N;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t titer = 0;
-        const uint32_t set_cols = (uint32_t)((nmain + q.ncorr) * q.Nc);
+        const uint32_t set_cols = (uint32_t)q.set_cols;
+        const int nacc = q.merge ? 2 * nused : nused + q.ncorr;
         // residual of this warp's first 16-column group, fetched one tile ahead (right after the previous tile consumed it) so its
         // HBM latency is hidden behind a tile
         float rnext[16];
@@ -585,9 +617,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
                 }
-                for (int a = 1; a < nused + q.ncorr; ++a) {      // remaining main accumulators, then the correction accumulator
+                for (int a = 1; a < nacc; ++a) {      // remaining accumulators: (main, correction) pairs or mains then the correction
                     uint32_t r[16];
-                    tmem_ld16(tacc + (uint32_t)((a < nused ? a : nmain) * q.Nc + c16 * 16), r);
+                    tmem_ld16(tacc + (uint32_t)((q.merge || a < nused ? a : nmain) * q.Nc + c16 * 16), r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
@@ -660,7 +692,7 @@ struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 
 static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
-    const size_t slot = (size_t)MMA_SLOT_BYTES * (prologue >= 2 ? 2 : 1) + (prologue == 2 ? 6 * MMA_TP * 4 : 0);
+    const size_t slot = prologue == 2 ? (size_t)MMA_P2_SLOT : (size_t)MMA_SLOT_BYTES * (prologue == 3 ? 2 : 1);
     const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 8) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
     const int ring_min = (prologue == 1 || prologue == 3) ? max(nkb, 2) : 2;  // LN needs all K blocks of a tile resident
@@ -765,8 +797,22 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     // spreads the K blocks over up to three main accumulators
     q.ncorr = (passes == 3 && nkb >= 2) ? 1 : 0;
     q.nmain = 1;
-    if (nkb >= 2) q.nmain = max(1, min(min(3, nkb), (512 / Nc) - q.ncorr));
-    const int set_cols = (q.nmain + q.ncorr) * Nc;
+    q.merge = (passes == 3 && nkb >= 2 && 2 * Nc <= 256) ? 1 : 0;
+    if (const char* e = getenv("FDN_MMA_MERGE")) q.merge = q.merge && atoi(e) != 0;
+    int set_cols;
+    if (q.merge) {
+        // (main, correction) pairs; prefer two accumulator sets (epilogue overlaps the next tile) as long as two pairs remain
+        q.nmain = max(1, min(min(3, nkb), 512 / (2 * Nc)));
+        if (q.nmain > 2 && 2 * (2 * q.nmain * Nc) > 512 && 2 * (2 * 2 * Nc) <= 512) q.nmain = 2;
+        q.ncorr = 0;
+        set_cols = 2 * q.nmain * Nc;
+        q.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * Nc) >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
+    } else {
+        if (nkb >= 2) q.nmain = max(1, min(min(3, nkb), (512 / Nc) - q.ncorr));
+        set_cols = (q.nmain + q.ncorr) * Nc;
+        q.idesc2 = q.idesc;
+    }
+    q.set_cols = set_cols;
     q.nbuf = 2 * set_cols <= 512 ? 2 : 1;
     // copy requests per tile: the TMA unit handles ~1 small bulk request per 64 cycles, so many-row tiles use cp.async instead
     // TMA bulk copies (one per 512-byte channel row) measured equal or faster than 16-byte cp.async for every layer shape once
