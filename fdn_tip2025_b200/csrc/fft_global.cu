@@ -542,17 +542,6 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// C ABI
-// ---------------------------------------------------------------------------------------------------
-static int rows_per_cta_for(int W) { return max(1, min(16, 8192 / W)); }              // ~4096 packed complex points per CTA
-static size_t rows_smem(int W, int rpc) { return ((size_t)2 * rpc * (W / 2 + 2) + W / 2) * sizeof(float2); }
-static int cols_per_cta_for(int H) {
-    int tc = 8;
-    while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;
-    return tc;
-}
-
 template <class K>
 static int set_smem(K kern, size_t bytes) {
     if (bytes > 227 * 1024) {
@@ -567,6 +556,19 @@ static int set_smem(K kern, size_t bytes) {
         }
     }
     return 0;
+}
+
+#include "fft_fast.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+static int rows_per_cta_for(int W) { return max(1, min(16, 8192 / W)); }              // ~4096 packed complex points per CTA
+static size_t rows_smem(int W, int rpc) { return ((size_t)2 * rpc * (W / 2 + 2) + W / 2) * sizeof(float2); }
+static int cols_per_cta_for(int H) {
+    int tc = 8;
+    while (tc > 1 && (size_t)2 * H * tc * sizeof(float2) > 160 * 1024) tc >>= 1;
+    return tc;
 }
 
 // Creates (and caches) the twiddle tables for lengths H and W.  Call once per shape before CUDA-graph capture.
@@ -586,11 +588,15 @@ FDN_API int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int
     FDN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0, "x must be 8-byte aligned");
     FftPlanDev PM, PW;
     FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM) == 0 && fdn_fft_get_plan(W, &PW) == 0, "plan creation failed");
+    int nrows = planes * H;
+    if (fft_fast_enabled()) {
+        int frc = fft_fast_rows_r2c(x, reinterpret_cast<float2*>(spec), W / 2, PM.tw, PW.tw, nrows, st);
+        if (frc != FFT_FAST_NONE) return frc;
+    }
     int rpc = rows_per_cta_for(W);
     size_t smem = rows_smem(W, rpc);
     int rc = set_smem(k_rows_r2c, smem);
     if (rc) return rc;
-    int nrows = planes * H;
     FDN_LAUNCH(k_rows_r2c, dim3(fdn_cdiv(nrows, rpc)), dim3(256), smem, st, x, reinterpret_cast<float2*>(spec), PM, PW.tw, nrows, rpc);
     return fdn_check_launch("k_rows_r2c");
 }
@@ -613,6 +619,10 @@ FDN_API int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int
     q.nrows = planes * H;
     q.rows_per_cta = rows_per_cta_for(W);
     q.rows_per_image = max(1, planes_per_image) * H;
+    if (fft_fast_enabled()) {
+        int frc = fft_fast_rows_c2r(q, W / 2, PM.tw, PW.tw, st);
+        if (frc != FFT_FAST_NONE) return frc;
+    }
     size_t smem = rows_smem(W, q.rows_per_cta);
     int rc = set_smem(k_rows_c2r, smem);
     if (rc) return rc;
@@ -648,6 +658,10 @@ FDN_API int fdn_fft_cols(const float* in, long long in_ps, int in_rs, float* out
     q.pha = pha;
     q.w_xa = w_xa;
     q.w_xp = w_xp;
+    if (fft_fast_enabled()) {
+        int frc = fft_fast_cols(q, H, P.tw, planes, st);
+        if (frc != FFT_FAST_NONE) return frc;
+    }
     size_t smem = ((size_t)2 * H * q.tc + H) * sizeof(float2);
     int rc = set_smem(k_cols, smem);
     if (rc) return rc;
