@@ -329,6 +329,89 @@ __device__ __forceinline__ void dw_apply16(const float r[6][6], const float* __r
         }
 }
 
+// 8 (x) by 4 (y) outputs per thread with three rolling input rows of ten values (two aligned float4 plus the two neighbours):
+// 24 load instructions per 32 outputs; used whenever W is a multiple of 8 (every FDformer level)
+__device__ __forceinline__ void dw_row10(const float* __restrict__ plane, int H, int W, int yy, int x0, float r[10]) {
+    if (yy >= 0 && yy < H) {
+        const float* p = plane + (size_t)yy * W + x0;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        r[0] = x0 > 0 ? p[-1] : 0.f;
+        r[1] = a.x; r[2] = a.y; r[3] = a.z; r[4] = a.w; r[5] = b.x; r[6] = b.y; r[7] = b.z; r[8] = b.w;
+        r[9] = x0 + 8 < W ? p[8] : 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) r[i] = 0.f;
+    }
+}
+__device__ __forceinline__ void dw_row8(const float (&r0)[10], const float (&r1)[10], const float (&r2)[10], const float (&k)[9], float (&o)[8]) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        float a = k[0] * r0[x];
+        a += k[1] * r0[x + 1]; a += k[2] * r0[x + 2];
+        a += k[3] * r1[x]; a += k[4] * r1[x + 1]; a += k[5] * r1[x + 2];
+        a += k[6] * r2[x]; a += k[7] * r2[x + 1]; a += k[8] * r2[x + 2];
+        o[x] = a;
+    }
+}
+
+// every output row is finished (activation / gate) and stored as soon as its third input row has arrived, so only the rolling
+// input rows are live: ~64 registers for the plain and GELU modes, ~100 for the gate (two input channels in flight)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                                                    int C, int H, int W, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*ceil(H/4)*(W/8)
+    if (i >= total) return;
+    const int W8 = W >> 3, H4 = (H + 3) >> 2;
+    const int x0 = (int)(i % W8) * 8;
+    long long t = i / W8;
+    const int y0 = (int)(t % H4) * 4;
+    t /= H4;
+    const int c = (int)(t % C);
+    const long long b = t / C;
+    const int ca = MODE == 2 ? (c >> 1) : c, cb = (C + c) >> 1;
+    const float* pa = in + ((size_t)b * C + ca) * H * W;
+    const float* pb = in + ((size_t)b * C + cb) * H * W;
+    float ka[9], kb[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        ka[j] = w[c * 9 + j];
+        kb[j] = MODE == 2 ? w[(C + c) * 9 + j] : 0.f;
+    }
+    float a0[10], a1[10], a2[10], b0[10], b1[10], b2[10];
+    dw_row10(pa, H, W, y0 - 1, x0, a0);
+    dw_row10(pa, H, W, y0, x0, a1);
+    if (MODE == 2) {
+        dw_row10(pb, H, W, y0 - 1, x0, b0);
+        dw_row10(pb, H, W, y0, x0, b1);
+    }
+    float* op = out + (((size_t)b * C + c) * H + y0) * W + x0;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        float o[8];
+        dw_row10(pa, H, W, y0 + y + 1, x0, a2);
+        dw_row8(a0, a1, a2, ka, o);
+        if (MODE >= 1) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) o[x] = fdn_gelu(o[x]);
+        }
+        if (MODE == 2) {
+            float o2[8];
+            dw_row10(pb, H, W, y0 + y + 1, x0, b2);
+            dw_row8(b0, b1, b2, kb, o2);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) o[x] *= o2[x];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { b0[j] = b1[j]; b1[j] = b2[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; }
+        if (y0 + y < H) {
+            *reinterpret_cast<float4*>(op + (size_t)y * W) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(op + (size_t)y * W + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_dwconv3(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                                                  int C, int H, int W, int mode, long long total) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*ceil(H/4)*(W/4)
@@ -373,6 +456,16 @@ FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int 
     FDN_REQUIRE(W % 4 == 0 && fdn_aligned16(out), "W must be a multiple of 4 and out 16-byte aligned");
     FDN_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
     FDN_REQUIRE(fdn_aligned16(in), "in must be 16-byte aligned");
+    if (W % 8 == 0 && !getenv("FDN_DWCONV_W4")) {
+        long long total8 = (long long)B * C * ((H + 3) / 4) * (W / 8);
+        dim3 grid(fdn_cdiv(total8, 128)), block(128);
+        static const int gate_occ = getenv("FDN_DW_GATE_OCC") ? atoi(getenv("FDN_DW_GATE_OCC")) : 4;
+        if (mode == 0) { auto k = k_dwconv3_w8<0, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
+        else if (mode == 1) { auto k = k_dwconv3_w8<1, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
+        else if (gate_occ == 5) { auto k = k_dwconv3_w8<2, 5>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
+        else { auto k = k_dwconv3_w8<2, 4>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
+        return fdn_check_launch("k_dwconv3_w8");
+    }
     long long total = (long long)B * C * ((H + 3) / 4) * (W / 4);
     FDN_LAUNCH_SEQ(k_dwconv3, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, in, w, out, C, H, W, mode, total);
     return fdn_check_launch("k_dwconv3");
