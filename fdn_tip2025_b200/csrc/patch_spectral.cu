@@ -229,17 +229,49 @@ __global__ void __launch_bounds__(128) k_fdffn_patch_dw(const float* __restrict_
 #ifndef FDSA_MIN_BLOCKS
 #define FDSA_MIN_BLOCKS 4
 #endif
+#ifdef FDN_EMU
+#define FDN_WARP_SYNC() __syncthreads()      // the emulator runs the lanes of a warp as free-running host threads
+#else
+#define FDN_WARP_SYNC() __syncwarp()
+#endif
+#define FDSA_IW 248        // floats of exchange space per item: 40 bins x 3 roles x float2 = 240, padded so that the eight items of a
+                           // warp land on distinct bank pairs (every 64-bit access of the exchange is the 2-wavefront minimum)
+
+// All three FDSA outputs of one bin (see fdsa_bin): out1 = |v'| e^{i dtheta}, out2 = |qk| e^{i angle v'}, out3 = |qk| e^{i dtheta}.
+__device__ __forceinline__ void fdsa_bin3(float2 q, float2 k, float2 v, float2& o1, float2& o2, float2& o3) {
+    float2 qk = cmul(q, k);
+    qk.x = fdn_rd(qk.x);
+    qk.y = fdn_rd(qk.y);
+    const float s = qk.x * qk.x + qk.y * qk.y;
+    const float A = s * rsqrtf(s);                                           // |rd(q k)|
+    const float2 qc = make_float2(fdn_rd(q.x), fdn_rd(q.y)), kc = make_float2(fdn_rd(k.x), fdn_rd(k.y));
+    const float iq = rsqrtf(qc.x * qc.x + qc.y * qc.y), ik = rsqrtf(kc.x * kc.x + kc.y * kc.y);
+    const float2 u = cmulc(make_float2(qc.x * iq, qc.y * iq), make_float2(kc.x * ik, kc.y * ik));   // e^{i(th_q - th_k)}
+    const float2 vc = make_float2(fdn_rd(v.x), fdn_rd(v.y));                 // v' = rd(v * fft)
+    const float sv = vc.x * vc.x + vc.y * vc.y, iv = rsqrtf(sv);
+    const float m = sv * iv, sc = A * iv;
+    o1 = make_float2(m * u.x, m * u.y);
+    o2 = make_float2(sc * vc.x, sc * vc.y);
+    o3 = make_float2(A * u.x, A * u.y);
+}
+
+// Four lanes per (channel, patch): q, k, v and v_value.  Each lane convolves its 10x10 halo window (to_hidden_dw) in registers and
+// the q/k/v lanes transform their patch.  The bin algebra needs q, k and v of a bin together, so the three spectra are exchanged
+// through shared memory and the 40 bins are split over the four lanes (ten each, the v_value lane included): every lane evaluates
+// all three outputs of its bins once - instead of every role lane re-deriving the shared moduli and phases of all 40 bins from
+// 240 shuffles - and the role lanes read their output spectrum back for the inverse transform.
 __global__ void __launch_bounds__(128, FDSA_MIN_BLOCKS) k_fdsa_patch_dw(const float* __restrict__ hid, const float* __restrict__ wdw,
                                                        const float* __restrict__ wfft, float* __restrict__ out, float* __restrict__ vv,
                                                        int E, int H, int W, long long nitems) {
+    __shared__ __align__(16) float s_x[4 * 8 * FDSA_IW];
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int t = lane >> 2, role = lane & 3;
     const long long item = warp * 8 + t;
     const bool valid = item < nitems;
     const int pw = W >> 3, ph = H >> 3;
+    float2* sx = reinterpret_cast<float2*>(s_x + ((threadIdx.x >> 5) * 8 + t) * FDSA_IW);
     float p[64];
-    float2 S[8][5];
     size_t off_out = 0;
     int e = 0;
     if (valid) {
@@ -261,21 +293,41 @@ __global__ void __launch_bounds__(128, FDSA_MIN_BLOCKS) k_fdsa_patch_dw(const fl
 #pragma unroll
         for (int i = 0; i < 64; ++i) p[i] = 0.f;
     }
-    rfft2_8x8(p, S);
-    const int l0 = 4 * t;
+    {
+        float2 S[8][5];
+        rfft2_8x8(p, S);
+        if (role < 3) {
 #pragma unroll
-    for (int ky = 0; ky < 8; ++ky)
+            for (int ky = 0; ky < 8; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            float wsel = (valid && role == 2) ? wfft[e * 40 + ky * 5 + kx] : 1.0f;
-            float sx = S[ky][kx].x * wsel, sy = S[ky][kx].y * wsel;
-            float2 q = make_float2(__shfl_sync(0xffffffffu, sx, l0), __shfl_sync(0xffffffffu, sy, l0));
-            float2 k = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 1), __shfl_sync(0xffffffffu, sy, l0 + 1));
-            float2 v = make_float2(__shfl_sync(0xffffffffu, sx, l0 + 2), __shfl_sync(0xffffffffu, sy, l0 + 2));
-            S[ky][kx] = fdsa_bin(q, k, v, role);
+                for (int kx = 0; kx < 5; ++kx) sx[(ky * 5 + kx) * 3 + role] = S[ky][kx];
         }
-    irfft2_8x8(S, p);
-    if (valid && role != 3) store_patch(out + off_out, W, p);
+    }
+    FDN_WARP_SYNC();
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int bin = 4 * j + role;
+        const float wv = valid ? wfft[e * 40 + bin] : 1.0f;
+        const float2 q = sx[bin * 3], k = sx[bin * 3 + 1];
+        float2 v = sx[bin * 3 + 2];
+        v.x *= wv;
+        v.y *= wv;
+        float2 o1, o2, o3;
+        fdsa_bin3(q, k, v, o1, o2, o3);
+        sx[bin * 3] = o1;
+        sx[bin * 3 + 1] = o2;
+        sx[bin * 3 + 2] = o3;
+    }
+    FDN_WARP_SYNC();
+    if (role < 3) {          // warp-divergent from here on: no synchronisation below
+        float2 S[8][5];
+#pragma unroll
+        for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) S[ky][kx] = sx[(ky * 5 + kx) * 3 + role];
+        irfft2_8x8(S, p);
+        if (valid) store_patch(out + off_out, W, p);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

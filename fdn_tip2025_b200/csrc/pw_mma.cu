@@ -33,7 +33,6 @@
 #include <type_traits>
 
 #ifndef FDN_EMU
-#include <cuda.h>      // CUtensorMap (the encoder is resolved through cudaGetDriverEntryPoint: no link against libcuda)
 
 #define MMA_TP 128          // pixels per tile (UMMA M)
 #define MMA_KB 32           // channels per K block (one 128-byte swizzle row of tf32)
@@ -91,9 +90,6 @@ struct PwMmaParams {
     int E;                  // prologue 2: channels per LayerNorm group (K is then laid out in blocks of 3 x 10 channels)
     int Kreal;              // number of real input channels (= K except for the grouped layout of prologue 2)
     unsigned long long* dbg;  // optional [8] counters: cycles each role spent waiting on each barrier (fdn_pw_mma_set_debug)
-    // bulk == 2: TMA tensor maps over [B][C][HW] fp32 (box = [rows][128 pixels]); one request per operand block instead of one
-    // per 512-byte channel row (the TMA unit accepts roughly one request per 64 cycles, which bounded the many-channel layers)
-    alignas(64) CUtensorMap map_src0, map_src1, map_aux, map_stats;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -146,11 +142,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -240,7 +231,7 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
 }
 
 template <int PRO, int PASSES>
-__global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(const __grid_constant__ PwMmaParams q) {
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align by pointer arithmetic on the shared array (an integer round trip would turn every access into a generic LD/ST)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -326,33 +317,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(const __grid_constant
                         bulk_g2s(s_stage + s * stage_bytes + 2 * a_bytes, bsrc + (size_t)kb * 2 * q.Nc * 32, bytes, &a_full[s]);
                     }
             }
-        } else if (q.bulk == 2) {
-            // TMA tensor maps: one request per [rows][128 pixel] box, issued by a single lane.  Boxes are always full size (rows or
-            // pixels outside the tensor arrive as zeros and still count towards the transaction bytes); rows that belong to another
-            // group or source are masked by the producers exactly as in the other loaders.
-            if (warp == MMA_LOAD_WARP0 && lane == 0)
-                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                    const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
-                    for (int kb = 0; kb < nkb; ++kb, ++lit) {
-                        const int r = lit % q.ring;
-                        if (lit >= (uint32_t)q.ring) mbar_wait_t(&raw_empty[r], ((lit / q.ring) - 1) & 1, &w0, rec);
-                        unsigned char* slot = s_raw + (size_t)r * slot_bytes;
-                        if (PRO == 2) {
-                            mbar_expect_tx(&raw_full[r], (uint32_t)(4 * MMA_EB + (kb == 0 ? 6 : 0)) * (MMA_TP * 4));
-#pragma unroll
-                            for (int g = 0; g < 3; ++g)
-                                tma_load_3d(slot + g * MMA_EB * (MMA_TP * 4), &q.map_src0, p0, g * q.E + kb * MMA_EB, b, &raw_full[r]);
-                            tma_load_3d(slot + MMA_P2_V_OFF, &q.map_aux, p0, kb * MMA_EB, b, &raw_full[r]);
-                            if (kb == 0) tma_load_3d(slot + MMA_P2_ST_OFF, &q.map_stats, p0, 0, b, &raw_full[r]);
-                        } else {
-                            mbar_expect_tx(&raw_full[r], (uint32_t)MMA_SLOT_BYTES * (has_aux ? 2 : 1));
-                            const int k0 = kb * MMA_KB;
-                            if (k0 < q.C0) tma_load_3d(slot, &q.map_src0, p0, k0, b, &raw_full[r]);
-                            else tma_load_3d(slot, &q.map_src1, p0, k0 - q.C0, b, &raw_full[r]);
-                            if (has_aux) tma_load_3d(slot + MMA_SLOT_BYTES, &q.map_aux, p0, k0, b, &raw_full[r]);
-                        }
-                    }
-                }
         } else if (q.bulk) {
             // one TMA bulk copy (512 contiguous bytes) per channel row.  Issuing a bulk copy costs ~60 cycles of one thread's
             // uniform datapath, so the rows of every K block are interleaved over all loader warps that do not stream weights.
@@ -755,34 +719,6 @@ static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
 }
 #endif  // !FDN_EMU
 
-#ifndef FDN_EMU
-typedef CUresult (*FdnEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static FdnEncodeTiled fdn_encode_tiled() {
-    static FdnEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<FdnEncodeTiled>(p);
-    }
-    return fn;
-}
-// [B][C][HW] fp32 tensor, batch stride bs elements; box = [1][rows][128 pixels] (pixels fastest)
-static bool fdn_make_map(CUtensorMap* m, const float* base, int B, int C, int HW, long long bs, int rows) {
-    FdnEncodeTiled enc = fdn_encode_tiled();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)bs * 4};
-    cuuint32_t box[3] = {(cuuint32_t)MMA_TP, (cuuint32_t)rows, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-#endif
-
 static unsigned long long* g_pw_mma_dbg = nullptr;
 // Development aid: device buffer of 8 uint64 counters that every following fdn_pw_mma launch adds its per-role wait cycles to
 // (NULL disables).  [0] producers on raw_full, [1] producers on a_empty, [2] epilogue on acc_full, [3] MMA on a_full,
@@ -882,26 +818,8 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     // TMA bulk copies (one per 512-byte channel row) measured equal or faster than 16-byte cp.async for every layer shape once
     // the gate prologue stopped re-loading v_value three times; cp.async stays selectable with FDN_MMA_BULK=0
     q.bulk = 1;
-    memset(&q.map_src0, 0, 4 * sizeof(CUtensorMap));
-    {
-        // Tensor-map loader (whole [rows][128 pixel] boxes; needs tiles of 128 pixels and a concatenated second source that starts
-        // on a K-block boundary).  Measured in the 1120x640 forward (4 images): FDSA project_out at level 2 (E = 76) 7.0 -> 5.1 ms,
-        // level 1 unchanged, level 3 (16 K blocks) +4 %, and the LayerNorm / plain prologues 10-40 % slower than per-row bulk
-        // copies spread over 64 lanes - so it is the default only for the gate prologue with at most 8 K blocks.
-        // FDN_MMA_BULK = 2 / 1 / 0 forces tensor maps / per-row bulk copies / 16-byte cp.async for every launch.
-        int want = (prologue == 2 && (c0 / 3 + MMA_EB - 1) / MMA_EB <= 8) ? 2 : 1;
-        if (const char* e = getenv("FDN_MMA_BULK")) want = atoi(e);
-        bool ok = want == 2 && HW >= MMA_TP && (!src1 || c0 % MMA_KB == 0);
-        if (ok) {
-            const int rows = prologue == 2 ? MMA_EB : MMA_KB;
-            ok = fdn_make_map(&q.map_src0, src0, B, q.C0, HW, (long long)q.C0 * HW, rows);
-            if (ok && src1) ok = fdn_make_map(&q.map_src1, src1, B, q.C1, HW, (long long)q.C1 * HW, rows);
-            if (ok && prologue == 2) ok = fdn_make_map(&q.map_aux, aux, B, q.E, HW, aux_bs, MMA_EB) && fdn_make_map(&q.map_stats, stats, B, 6, HW, 6LL * HW, 6);
-            if (ok && prologue == 3) ok = fdn_make_map(&q.map_aux, aux, B, q.Kreal, HW, aux_bs, MMA_KB);
-        }
-        q.bulk = ok ? 2 : (want == 0 ? 0 : 1);
-    }
     if (const char* e = getenv("FDN_MMA_NBUF")) { if (atoi(e) == 1) { q.nbuf = 1; q.tmem_cols = 32; while (q.tmem_cols < set_cols) q.tmem_cols <<= 1; } }
+    if (const char* e = getenv("FDN_MMA_BULK")) q.bulk = atoi(e);
     q.tmem_cols = 32;
     while (q.tmem_cols < q.nbuf * set_cols) q.tmem_cols <<= 1;
     FDN_REQUIRE(q.tmem_cols <= 512, "accumulators do not fit in tensor memory");

@@ -280,7 +280,7 @@ def case_lpnet(dev, h, w, report=None, sd=None):
         compare("LPNet %dx%d ori=%s" % (h, w, ori), got, ref, rel_l2=1e-5, max_rel=1e-5, report=report)
 
 
-def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True):
+def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03):
     """End-to-end gate with damped weights against the fp64 oracle.
 
     strict: the north-star gate, max-abs <= 1e-3 and PSNR >= 50 dB.
@@ -292,7 +292,7 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True):
     on a few patches while every block matches the fp64 oracle to 1e-6 on generic inputs.
     """
     dim, variant = (32, "lolblur") if kind == "FDN" else (24, "lolv1")
-    sd = synth.fdn_state_dict(dim=dim, seed=seed, damp=0.03)
+    sd = synth.fdn_state_dict(dim=dim, seed=seed, damp=damp)
     net = getattr(archs, kind)()
     net.load_state_dict(sd, strict=True)
     net = net.to(dev)
