@@ -24,23 +24,26 @@ struct ConvParams {
 
 #define CV_TX 16   // threads along x, 4 outputs each
 #define CV_TY 16   // threads along y
-#define CV_NO 8    // output channels per CTA
 
-template <int K, int S>
+// NO = output channels per CTA (16 for the wide FDformer convs: the staged input tile is reused twice as often and a thread has
+// 64 independent accumulators; 8 for the narrow MAR / LPNet layers).  The staged input rows are padded to a multiple of four
+// floats so that, at stride 1, a thread reads its K+3 wide window with one conflict-free 128-bit load plus the K-1 values after
+// it - once per kernel row, reused by all K taps - instead of four 4-way-conflicting scalar loads per tap.
+template <int K, int S, int NO>
 __global__ void __launch_bounds__(256) k_conv2d(ConvParams q) {
     FDN_DYN_SMEM(smem);
     constexpr int TW = CV_TX * 4, TH = CV_TY;                 // output tile
-    constexpr int IW = (TW - 1) * S + K, IH = (TH - 1) * S + K;   // input tile
-    float* Ws = reinterpret_cast<float*>(smem);               // [cc][K][K][CV_NO]  (first: keeps float4 reads aligned)
-    float* Is = Ws + q.cc * K * K * CV_NO;                    // [cc][IH][IW]
+    constexpr int IW = ((TW - 1) * S + K + 3) & ~3, IH = (TH - 1) * S + K;   // input tile (row stride padded to 16 bytes)
+    float* Ws = reinterpret_cast<float*>(smem);               // [cc][K][K][NO]  (first: keeps float4 reads aligned)
+    float* Is = Ws + q.cc * K * K * NO;                       // [cc][IH][IW]
     const int tid = threadIdx.x, tx = tid % CV_TX, ty = tid / CV_TX;
     const int tiles_x = (q.Wout + TW - 1) / TW;
     const int ox0 = (blockIdx.x % tiles_x) * TW, oy0 = (blockIdx.x / tiles_x) * TH;
-    const int co0 = blockIdx.y * CV_NO, b = blockIdx.z;
+    const int co0 = blockIdx.y * NO, b = blockIdx.z;
     const int ix0 = ox0 * S - q.pad, iy0 = oy0 * S - q.pad;
-    float acc[CV_NO][4];
+    float acc[NO][4];
 #pragma unroll
-    for (int o = 0; o < CV_NO; ++o)
+    for (int o = 0; o < NO; ++o)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[o][j] = 0.f;
 
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(256) k_conv2d(ConvParams q) {
                 v = q.in[(((size_t)b * q.Cin + c0 + c) * q.Hin + gy) * q.Win + gx];
             Is[i] = v;
         }
-        for (int i = tid; i < nc * K * K * CV_NO; i += 256) {
-            int o = i % CV_NO, r = i / CV_NO;
+        for (int i = tid; i < nc * K * K * NO; i += 256) {
+            int o = i % NO, r = i / NO;
             int kk = r % (K * K), c = r / (K * K);
             int co = co0 + o;
             Ws[i] = co < q.Cout ? q.w[((size_t)co * q.Cin + c0 + c) * K * K + kk] : 0.f;
@@ -64,29 +67,40 @@ __global__ void __launch_bounds__(256) k_conv2d(ConvParams q) {
         __syncthreads();
         for (int c = 0; c < nc; ++c) {
             const float* ip = Is + c * IH * IW + (ty * S) * IW + (tx * 4) * S;
-            const float* wp = Ws + c * K * K * CV_NO;
+            const float* wp = Ws + c * K * K * NO;
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky)
+            for (int ky = 0; ky < K; ++ky) {
+                float win[S == 1 ? K + 3 : 1];
+                if (S == 1) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(ip + ky * IW);
+                    win[0] = w4.x; win[1] = w4.y; win[2] = w4.z; win[3] = w4.w;
+#pragma unroll
+                    for (int j = 4; j < K + 3; ++j) win[S == 1 ? j : 0] = ip[ky * IW + j];
+                }
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    float4 w0 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * CV_NO);
-                    float4 w1 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * CV_NO + 4);
-                    float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float wv[NO];
+#pragma unroll
+                    for (int o = 0; o < NO; o += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wp + (ky * K + kx) * NO + o);
+                        wv[o] = w4.x; wv[o + 1] = w4.y; wv[o + 2] = w4.z; wv[o + 3] = w4.w;
+                    }
                     float xv[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) xv[j] = ip[ky * IW + j * S + kx];
+                    for (int j = 0; j < 4; ++j) xv[j] = S == 1 ? win[S == 1 ? j + kx : 0] : ip[ky * IW + j * S + kx];
 #pragma unroll
-                    for (int o = 0; o < CV_NO; ++o)
+                    for (int o = 0; o < NO; ++o)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) acc[o][j] += wv[o] * xv[j];
                 }
+            }
         }
         __syncthreads();
     }
     const int oy = oy0 + ty;
     if (oy >= q.Hout) return;
 #pragma unroll
-    for (int o = 0; o < CV_NO; ++o) {
+    for (int o = 0; o < NO; ++o) {
         int co = co0 + o;
         if (co >= q.Cout) continue;
         float bias = q.bias ? q.bias[co] : 0.f;
@@ -138,21 +152,26 @@ __global__ void k_conv2d_naive(ConvParams q, int K, int S, long long total) {
     q.out[i] = v;
 }
 
-template <int K, int S>
-static int launch_conv(ConvParams& q, cudaStream_t st) {
-    constexpr int IW = (CV_TX * 4 - 1) * S + K, IH = (CV_TY - 1) * S + K;
-    size_t per_c = (size_t)(IH * IW + K * K * CV_NO) * sizeof(float);
+template <int K, int S, int NO>
+static int launch_conv_no(ConvParams& q, cudaStream_t st) {
+    constexpr int IW = ((CV_TX * 4 - 1) * S + K + 3) & ~3, IH = (CV_TY - 1) * S + K;
+    size_t per_c = (size_t)(IH * IW + K * K * NO) * sizeof(float);
     int cc = (int)min((size_t)q.Cin, max((size_t)1, (size_t)(64 * 1024) / per_c));
     q.cc = cc;
     size_t smem = per_c * cc;
-    auto kern = k_conv2d<K, S>;
+    auto kern = k_conv2d<K, S, NO>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
     }
     int tiles = fdn_cdiv(q.Wout, CV_TX * 4) * fdn_cdiv(q.Hout, CV_TY);
-    FDN_LAUNCH(kern, dim3(tiles, fdn_cdiv(q.Cout, CV_NO), q.B), dim3(256), smem, st, q);
+    FDN_LAUNCH(kern, dim3(tiles, fdn_cdiv(q.Cout, NO), q.B), dim3(256), smem, st, q);
     return fdn_check_launch("k_conv2d");
+}
+template <int K, int S>
+static int launch_conv(ConvParams& q, cudaStream_t st) {
+    if (K == 3 && q.Cout >= 16 && q.Cout % 16 == 0) return launch_conv_no<K, S, 16>(q, st);
+    return launch_conv_no<K, S, 8>(q, st);
 }
 
 // Dense KxK convolution, groups=1.  y = act(conv(x)+bias) + res           (head = 0)

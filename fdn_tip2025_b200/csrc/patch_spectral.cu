@@ -195,7 +195,7 @@ __device__ __forceinline__ void dw3_patch_add(const float* __restrict__ plane, c
 
 // FDFFN: out = irfft2(rd(rfft2(h)) * wspec[c]) + dw_b(s1)      - the second depthwise conv of the spatial branch
 // (space.2, FDN_arch.py:439-441,457) is evaluated on the patch from s1 with a one-pixel halo, so s2 never exists in HBM.
-__global__ void __launch_bounds__(128) k_fdffn_patch_dw(const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ wb,
+__global__ void __launch_bounds__(128, 4) k_fdffn_patch_dw(const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ wb,
                                                         const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W,
                                                         long long nitems) {
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
