@@ -47,6 +47,8 @@ SIGNATURES = {
     "fdn_se_apply": "ppppiis",
     "fdn_lpnet_head": "pppppppiis",
     "fdn_gray_mean": "ppiis",
+    "fdn_pre_u8hwc_to_f32chw": "ppiiiiis",
+    "fdn_post_f32chw_to_u8hwc": "ppiiiiis",
 }
 _CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P}
 

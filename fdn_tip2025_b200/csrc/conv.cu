@@ -300,9 +300,73 @@ __global__ void k_convt4s2(const float* __restrict__ in, const float* __restrict
     out[i] = fdn_act(acc, act);
 }
 
+// Gather form for the MAR up-samplers (Cin <= 48, Cout a multiple of 12): a thread owns one input position and produces the 2x2
+// output block it maps to, for 12 output channels, from the 3x3 input neighbourhood (9 coalesced loads per input channel feed
+// 192 FMAs); the weights of the channel group are broadcast from shared memory.  Even output rows take kernel rows 1 (same input
+// row) and 3 (row above), odd rows take 2 (same row) and 0 (row below); columns alike.
+#define CT_CO 12
+#define CT_MAXCIN 48
+__global__ void __launch_bounds__(256) k_convt4s2_g(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                    float* __restrict__ out, int Cin, int Cout, int H, int W, int act, long long total) {
+    __shared__ __align__(16) float sw[CT_MAXCIN * CT_CO * 16];          // [cin][co][ky][kx]
+    const int co0 = blockIdx.y * CT_CO;
+    for (int i = threadIdx.x; i < Cin * CT_CO * 16; i += 256) {
+        const int c = i / (CT_CO * 16), r = i - c * (CT_CO * 16);
+        sw[i] = w[((size_t)c * Cout + co0) * 16 + r];
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*H*W
+    if (i >= total) return;
+    const int ix = (int)(i % W);
+    long long t = i / W;
+    const int iy = (int)(t % H);
+    const long long b = t / H;
+    float acc[CT_CO][4];
+#pragma unroll
+    for (int o = 0; o < CT_CO; ++o) {
+        const float bv = bias ? bias[co0 + o] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[o][j] = bv;
+    }
+    const bool up = iy > 0, dn = iy + 1 < H, lf = ix > 0, rt = ix + 1 < W;
+    for (int c = 0; c < Cin; ++c) {
+        const float* p = in + (((size_t)b * Cin + c) * H + iy) * W + ix;
+        float n[3][3];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const bool ok = (dy == 1 || (dy == 0 ? up : dn)) && (dx == 1 || (dx == 0 ? lf : rt));
+                n[dy][dx] = ok ? p[(dy - 1) * W + (dx - 1)] : 0.f;
+            }
+        const float4* wc = reinterpret_cast<const float4*>(sw + c * CT_CO * 16);
+#pragma unroll
+        for (int o = 0; o < CT_CO; ++o) {
+            const float4 k0 = wc[o * 4 + 0], k1 = wc[o * 4 + 1], k2 = wc[o * 4 + 2], k3 = wc[o * 4 + 3];     // kernel rows 0..3
+            // output (a, b2) = (row parity, column parity); rows: a=0 -> ky 1 (n[1]) + ky 3 (n[0]); a=1 -> ky 2 (n[1]) + ky 0 (n[2])
+            acc[o][0] += n[1][1] * k1.y + n[1][0] * k1.w + n[0][1] * k3.y + n[0][0] * k3.w;      // even row, even col: kx 1 (same), kx 3 (left)
+            acc[o][1] += n[1][1] * k1.z + n[1][2] * k1.x + n[0][1] * k3.z + n[0][2] * k3.x;      // even row, odd col: kx 2 (same), kx 0 (right)
+            acc[o][2] += n[1][1] * k2.y + n[1][0] * k2.w + n[2][1] * k0.y + n[2][0] * k0.w;      // odd row, even col
+            acc[o][3] += n[1][1] * k2.z + n[1][2] * k2.x + n[2][1] * k0.z + n[2][2] * k0.x;      // odd row, odd col
+        }
+    }
+    const int Wo = 2 * W, Ho = 2 * H;
+#pragma unroll
+    for (int o = 0; o < CT_CO; ++o) {
+        float* op = out + (((size_t)b * Cout + co0 + o) * Ho + 2 * iy) * Wo + 2 * ix;
+        *reinterpret_cast<float2*>(op) = make_float2(fdn_act(acc[o][0], act), fdn_act(acc[o][1], act));
+        *reinterpret_cast<float2*>(op + Wo) = make_float2(fdn_act(acc[o][2], act), fdn_act(acc[o][3], act));
+    }
+}
+
 FDN_API int fdn_convt4s2(const float* in, const float* w, const float* bias, float* out, int B, int Cin, int Cout, int H, int W,
                          int act, cudaStream_t st) {
     FDN_REQUIRE(in && w && out && B > 0 && Cin > 0 && Cout > 0, "bad arguments");
+    if (Cin <= CT_MAXCIN && Cout % CT_CO == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        long long npos = (long long)B * H * W;
+        FDN_LAUNCH(k_convt4s2_g, dim3(fdn_cdiv(npos, 256), Cout / CT_CO), dim3(256), 0, st, in, w, bias, out, Cin, Cout, H, W, act, npos);
+        return fdn_check_launch("k_convt4s2_g");
+    }
     long long total = (long long)B * Cout * H * W * 4;
     FDN_LAUNCH_SEQ(k_convt4s2, dim3(fdn_cdiv(total, 256)), dim3(256), 0, st, in, w, bias, out, Cin, Cout, H, W, act, total);
     return fdn_check_launch("k_convt4s2");

@@ -220,3 +220,22 @@ def lpnet_head(m, w1, b1, w2, b2, gray, out):
 def gray_mean(x, out):
     b, _, h, w = x.shape
     _lib.call("fdn_gray_mean", _p(x), _p(out), b, h * w, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ image pre/post (inference scripts)
+def _pu8(t):
+    _device_ok(t)
+    assert t.dtype == torch.uint8 and t.is_contiguous(), "image buffers are contiguous uint8"
+    return t.data_ptr()
+
+
+def pre_u8hwc(img, out):
+    """img [B,h,w,3] uint8 BGR -> out [B,3,Hp,Wp] fp32 RGB in [0,1], reflect-padded (inference_fdn_lolblur.py:47-62)."""
+    b, h, w, _ = img.shape
+    _lib.call("fdn_pre_u8hwc_to_f32chw", _pu8(img), _p(out), b, h, w, out.shape[2], out.shape[3], _stream())
+
+
+def post_u8hwc(x, img):
+    """x [B,3,Hp,Wp] fp32 RGB -> img [B,h,w,3] uint8 BGR: crop, clamp, *255, round (tensor2img, img_util.py:36-98)."""
+    b, h, w, _ = img.shape
+    _lib.call("fdn_post_f32chw_to_u8hwc", _p(x), _pu8(img), b, h, w, x.shape[2], x.shape[3], _stream())

@@ -156,6 +156,15 @@ int fdn_lpnet_head(const float* m, const float* w1, const float* b1, const float
                    float* out, int B, int C, cudaStream_t st);
 int fdn_gray_mean(const float* x, float* out, int B, int HW, cudaStream_t st);
 
+/* ---- image pre/post-processing of the inference scripts (the steps either side of the forward) -----------------------------
+ * fdn_pre_u8hwc_to_f32chw: cv2.imread bytes [B][h][w][3] uint8 BGR -> [B][3][Hp][Wp] fp32 RGB in [0,1] (astype(float32)/255,
+ *   img2tensor(bgr2rgb=True) basicsr/utils/img_util.py:9-33) with F.pad(..., (0, Wp-w, 0, Hp-h), 'reflect')
+ *   (inference_fdn_lolblur.py:47-62, inference_fdn_lolv1.py:44-57).  Requires Hp-h < h and Wp-w < w like torch.
+ * fdn_post_f32chw_to_u8hwc: [B][3][Hp][Wp] fp32 RGB -> [B][h][w][3] uint8 BGR: crop [:h,:w], clamp [0,1], *255, round half to
+ *   even (tensor2img(rgb2bgr=True) img_util.py:36-98; inference_fdn_lolblur.py:72-73). */
+int fdn_pre_u8hwc_to_f32chw(const unsigned char* img, float* out, int B, int h, int w, int Hp, int Wp, cudaStream_t st);
+int fdn_post_f32chw_to_u8hwc(const float* x, unsigned char* img, int B, int h, int w, int Hp, int Wp, cudaStream_t st);
+
 #ifdef __cplusplus
 }
 #endif

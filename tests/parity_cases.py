@@ -147,6 +147,14 @@ def case_convt_dw_misc(dev):
     sync(dev)
     ref = F.leaky_relu(F.conv_transpose2d(x.float().double(), wgt.float().double(), bias.float().double(), stride=2, padding=1), 0.1)
     compare("convt4s2", out, ref, rel_l2=2e-6, max_rel=5e-6)
+    # MAR up-sampler shapes (Cout multiple of 12 -> gather kernel), odd spatial size to hit every border case
+    for cin, cout in ((24, 12), (48, 24)):
+        x, wgt, bias = rnd(b, cin, 7, 10, seed=4), rnd(cin, cout, 4, 4, seed=5), rnd(cout, seed=6)
+        out = torch.empty(b, cout, 14, 20, device=dev)
+        ops.convt4s2(dev32(x, dev), dev32(wgt, dev), dev32(bias, dev), out, act=1)
+        sync(dev)
+        ref = F.leaky_relu(F.conv_transpose2d(x.float().double(), wgt.float().double(), bias.float().double(), stride=2, padding=1), 0.1)
+        compare("convt4s2 %d->%d" % (cin, cout), out, ref, rel_l2=2e-6, max_rel=5e-6)
     c = 7
     x = rnd(b, c, 10, 16, seed=4)
     for mode in (0, 1):
@@ -317,6 +325,40 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03):
         for g, r in zip(got[1:], ref[1:]):
             assert (g.double().cpu() - r).abs().max().item() <= 1e-3      # MAR outputs are well conditioned
     return mx, ps
+
+
+# ----------------------------------------------------------------------------------------- image pre/post (inference scripts)
+def script_pre(img_u8):
+    """inference_fdn_lolblur.py:47-62 on the host: uint8 [B,h,w,3] BGR -> fp32 [B,3,Hp,Wp] RGB, reflect-padded to x32."""
+    import numpy as np
+    a = img_u8.numpy().astype(np.float32) / 255.
+    t = torch.from_numpy(np.ascontiguousarray(a[..., ::-1])).permute(0, 3, 1, 2).contiguous()      # cv2.COLOR_BGR2RGB, HWC -> CHW
+    h, w = t.shape[-2:]
+    return torch.nn.functional.pad(t, (0, (32 - w % 32) % 32, 0, (32 - h % 32) % 32), mode="reflect")
+
+
+def script_post(x, h, w):
+    """inference_fdn_lolblur.py:72-73 + tensor2img (img_util.py:36-98): fp32 [B,3,Hp,Wp] -> uint8 [B,h,w,3] BGR."""
+    import numpy as np
+    t = x[:, :, :h, :w].float().cpu().clamp(0, 1).numpy().transpose(0, 2, 3, 1)[..., ::-1]
+    return torch.from_numpy(np.ascontiguousarray((t * 255.0).round().astype(np.uint8)))
+
+
+def case_imgio(dev, h=50, w=70, b=2):
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = torch.randint(0, 256, (b, h, w, 3), generator=g, dtype=torch.uint8)
+    ref = script_pre(img)
+    out = torch.empty(ref.shape, dtype=torch.float32, device=dev)
+    ops.pre_u8hwc(img.to(dev), out)
+    sync(dev)
+    assert torch.equal(out.cpu(), ref), "pre-processing is not bit-exact"
+    x = torch.rand(ref.shape, generator=g) * 1.4 - 0.2                      # exercises both clamps
+    x[0, 0, 0, :4] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255])   # ties: round half to even
+    want = script_post(x, h, w)
+    got = torch.empty(b, h, w, 3, dtype=torch.uint8, device=dev)
+    ops.post_u8hwc(x.to(dev), got)
+    sync(dev)
+    assert torch.equal(got.cpu(), want), "post-processing is not bit-exact"
 
 
 # ----------------------------------------------------------------------------------------- tcgen05 1x1 convolution

@@ -41,3 +41,8 @@ def test_emu_fuse(emu):
 def test_emu_fdffn_fused_variant(emu, monkeypatch):
     monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
     P.case_tblock(emu, 32, 8, 16, False, False, seed=21)
+
+
+def test_emu_image_pre_post(emu):
+    P.case_imgio(emu)
+    P.case_imgio(emu, h=33, w=64, b=1)

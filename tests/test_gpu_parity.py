@@ -180,3 +180,50 @@ def test_fdffn_fused_variant(cuda_dev, monkeypatch):
     monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
     P.case_tblock(cuda_dev, 32, 40, 72, False, False, seed=21)      # ragged 32x32 tiles
     P.case_tblock(cuda_dev, 64, 32, 32, False, False, seed=22)
+
+
+def test_image_pre_post_bit_exact(cuda_dev):
+    """uint8 HWC BGR <-> fp32 CHW RGB, reflect pad, crop, clamp, round: bit-exact against the scripts' host code."""
+    P.case_imgio(cuda_dev)
+    P.case_imgio(cuda_dev, h=400, w=600, b=1)        # LOL-v1 frame -> 416x608
+    P.case_imgio(cuda_dev, h=33, w=64, b=3)
+
+
+@pytest.mark.parametrize("variant,kind", [("lolblur", "FDN"), ("lolv1", "FDN_lolv1")])
+def test_inference_pipeline_matches_script_semantics(cuda_dev, variant, kind):
+    """InferencePipeline (uint8 in, uint8 out, everything on the device) against the script's own sequence of host steps around the
+    same modules - must be bit-identical - and against the fp64 oracle run through the same steps (at most 1 LSB, rarely)."""
+    from fdn_tip2025_b200 import archs, pipeline, synth
+    h, w = 50, 70
+    dim = 32 if kind == "FDN" else 24
+    sd = synth.fdn_state_dict(dim=dim, seed=4, damp=0.005)
+    net = getattr(archs, kind)()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_dev).eval()
+    lsd = synth.lpnet_state_dict(seed=3)
+    lp = archs.I_predict_net()
+    lp.load_state_dict(lsd, strict=True)
+    lp = lp.to(cuda_dev).eval()
+    img = (synth.low_light_images(1, h, w)[0].permute(1, 2, 0) * 255).round().to(torch.uint8).flip(-1).contiguous()   # BGR frame
+    got = torch.from_numpy(pipeline.InferencePipeline(net, lp, variant)(img.numpy()))
+    # the script's host steps around our modules
+    x = P.script_pre(img[None]).to(cuda_dev)
+    ratio = lp(x)
+    if variant == "lolv1":
+        gray = (0.2989 * x[:, 0] + 0.587 * x[:, 1] + 0.114 * x[:, 2]).mean(dim=(1, 2)).view(1, 1)
+        ratio_in = gray / ratio
+    else:
+        ratio_in = ratio
+    want = P.script_post(net(x, ratio_i=ratio_in)[0], h, w)[0]
+    if variant == "lolblur":
+        assert torch.equal(got, want)
+    else:       # the gray mean is reduced in a different order on the device: allow the last bit of ratio_i to differ
+        assert (got.int() - want.int()).abs().max().item() <= 1
+    # fp64 oracle through the same steps
+    x64 = P.script_pre(img[None]).double()
+    r64 = P.O.lpnet(x64, P.O.to_dtype(lsd, torch.float64))
+    if variant == "lolv1":
+        r64 = (0.2989 * x64[:, 0] + 0.587 * x64[:, 1] + 0.114 * x64[:, 2]).mean(dim=(1, 2)).view(1, 1) / r64
+    ref = P.script_post(P.O.fdn(x64, r64, P._sd64(sd), variant)[0], h, w)[0]
+    d = (got.int() - ref.int()).abs()
+    assert d.max().item() <= 1 and (d > 0).float().mean().item() <= 1e-2

@@ -7,7 +7,8 @@ from fdn_tip2025_b200 import ops, packing, _lib
 B = 4
 dev = "cuda"
 shapes = [("L1 to_hidden", 716800, 32, 152, 1), ("L1 fdsa_out", 716800, 114, 32, 2), ("L1 ffn_in", 716800, 32, 86, 1), ("L1 ffn_out", 716800, 86, 32, 0),
-          ("L2 to_hidden", 179200, 64, 304, 1), ("L3 to_hidden", 44800, 128, 612, 1), ("L3 fdsa_out", 44800, 459, 128, 2)]
+          ("L2 to_hidden", 179200, 64, 304, 1), ("L2 fdsa_out", 179200, 228, 64, 2), ("L2 ffn_out", 179200, 172, 64, 0),
+          ("L3 to_hidden", 44800, 128, 612, 1), ("L3 fdsa_out", 44800, 459, 128, 2), ("L3 ffn_in", 44800, 128, 345, 1), ("L3 ffn_out", 44800, 345, 128, 0)]
 dbg = torch.zeros(8, dtype=torch.int64, device=dev)
 for name, hw, k, n, pro in shapes:
     h, w = 640, hw // 640
