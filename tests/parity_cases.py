@@ -295,7 +295,7 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03):
     not strict: PSNR >= 50 dB, max-abs <= 5e-2 and at most 5 % of the values off by more than 1e-3.  The network is
     chaotic at isolated FDSA bins: a purely real (self-conjugate) 8x8 bin of q or k that happens to be ~1e-7 gets its
     SIGN - a phase of 0 vs pi - from fp32 rounding noise (torch's own fp32 FFT has 100 % relative error there; see
-    tools/block0_check.py and DESIGN.md).  Any two fp32 evaluation orders - the reference on 1 vs 8 threads, the fp32
+    tests/tools/block0_check.py and DESIGN.md).  Any two fp32 evaluation orders - the reference on 1 vs 8 threads, the fp32
     oracle vs the reference (tests/test_oracle_golden.py), FFMA vs tensor-core GEMMs - therefore differ by a few 1e-3
     on a few patches while every block matches the fp64 oracle to 1e-6 on generic inputs.
     """

@@ -1,6 +1,6 @@
 """First FDSA block on a real (smooth, low-light) input: both GEMM modes against the fp64 oracle.  Dev tool, GPU only."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from fdn_tip2025_b200 import archs, synth, ops
 from oracle import fdn_oracle as O

@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import parity_cases as P
 for (k, n, pro) in ((32, 152, 1), (114, 32, 2), (32, 32, 3), (86, 32, 0), (32, 86, 1), (64, 304, 1), (228, 64, 2), (128, 612, 1), (459, 128, 2)):
     for hw in ((128, 160), (64, 80), (256, 320)):

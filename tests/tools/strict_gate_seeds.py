@@ -1,12 +1,13 @@
 """End-to-end strict gate (max-abs <= 1e-3 vs the fp64 oracle) over several weight seeds, FFMA GEMMs.  Shows how often isolated
 chaotic FDSA events push an fp32 evaluation order over 1e-3, for the fast and the generic FFT kernels.
-    FDN_FFT_FAST=0|1 python tools/strict_gate_seeds.py"""
+    FDN_FFT_FAST=0|1 python tests/tools/strict_gate_seeds.py"""
 import os
 import sys
 
 os.environ["FDN_B200_GEMM"] = "ffma"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 import parity_cases as P
 
