@@ -480,8 +480,28 @@ struct SpecMlpParams {
     const float* w;           // packed: W1m[NC*NC] b1m[NC] W2m[NC*NC] b2m[NC] W1p b1p W2p b2p   (row-major [out][in])
 };
 
+// y[n] = b[n] + sum_k W[n][k] x[k] with the weight row read as 128-bit broadcasts (4 FMAs per shared-memory load)
+template <int NC>
+__device__ __forceinline__ void mlp_layer(const float* __restrict__ W, const float* __restrict__ b, const float (&x)[NC], float (&y)[NC]) {
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        float acc = b[n];
+        const float4* w4 = reinterpret_cast<const float4*>(W + n * NC);
+#pragma unroll
+        for (int k = 0; k < NC / 4; ++k) {
+            const float4 w = w4[k];
+            acc += w.x * x[4 * k];
+            acc += w.y * x[4 * k + 1];
+            acc += w.z * x[4 * k + 2];
+            acc += w.w * x[4 * k + 3];
+        }
+        y[n] = acc;
+    }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
+    static_assert(NC % 4 == 0, "rows are read as float4");
     __shared__ __align__(16) float sw[4 * (NC * NC + NC)];
     for (int i = threadIdx.x; i < 4 * (NC * NC + NC); i += blockDim.x) sw[i] = q.w[i];
     __syncthreads();
@@ -504,40 +524,24 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
         float2 v = z[(size_t)c * q.plane_stride];
         in[c] = sqrtf(v.x * v.x + v.y * v.y);
     }
+    mlp_layer<NC>(W1m, b1m, in, hid);
 #pragma unroll
-    for (int n = 0; n < NC; ++n) {
-        float acc = b1m[n];
-#pragma unroll
-        for (int k = 0; k < NC; ++k) acc += W1m[n * NC + k] * in[k];
-        hid[n] = fdn_lrelu(acc);
-    }
-#pragma unroll
-    for (int n = 0; n < NC; ++n) {
-        float acc = b2m[n];
-#pragma unroll
-        for (int k = 0; k < NC; ++k) acc += W2m[n * NC + k] * hid[k];
-        om[n] = acc;
-    }
+    for (int n = 0; n < NC; ++n) hid[n] = fdn_lrelu(hid[n]);
+    mlp_layer<NC>(W2m, b2m, hid, om);
     // phase path
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         float2 v = z[(size_t)c * q.plane_stride];
         in[c] = atan2f(v.y, v.x);
     }
+    mlp_layer<NC>(W1p, b1p, in, hid);
+#pragma unroll
+    for (int n = 0; n < NC; ++n) hid[n] = fdn_lrelu(hid[n]);
+    mlp_layer<NC>(W2p, b2p, hid, in);
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
-        float acc = b1p[n];
-#pragma unroll
-        for (int k = 0; k < NC; ++k) acc += W1p[n * NC + k] * in[k];
-        hid[n] = fdn_lrelu(acc);
-    }
-#pragma unroll
-    for (int n = 0; n < NC; ++n) {
-        float acc = b2p[n];
-#pragma unroll
-        for (int k = 0; k < NC; ++k) acc += W2p[n * NC + k] * hid[k];
         float sn, cs;
-        sincosf(acc, &sn, &cs);
+        sincosf(in[n], &sn, &cs);
         z[(size_t)n * q.plane_stride] = make_float2(om[n] * cs, om[n] * sn);
     }
 }
