@@ -197,16 +197,15 @@ __device__ __forceinline__ void dw3_patch_add(const float* __restrict__ plane, c
 // (space.2, FDN_arch.py:439-441,457) is evaluated on the patch from s1 with a one-pixel halo, so s2 never exists in HBM.
 __global__ void __launch_bounds__(128, 4) k_fdffn_patch_dw(const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ wb,
                                                         const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W,
-                                                        long long nitems) {
-    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= nitems) return;
-    const int pw = W >> 3, ph = H >> 3;
-    int px = (int)(item % pw);
-    long long t = item / pw;
-    int py = (int)(t % ph);
-    long long plane = t / ph;              // b*C + c
-    int c = (int)(plane % C);
-    size_t off = (size_t)plane * H * W + (size_t)(py * 8) * W + px * 8;
+                                                        int per_plane) {
+    // grid.y = plane (b*C + c): channel, spectral weights and depthwise taps are uniform over the CTA
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;     // over (H/8)*(W/8)
+    if (item >= per_plane) return;
+    const int pw = W >> 3;
+    const int px = item % pw, py = item / pw;
+    const size_t plane = blockIdx.y;
+    const int c = blockIdx.y % C;
+    size_t off = plane * H * W + (size_t)(py * 8) * W + px * 8;
     float p[64];
     {
         float2 S[8][5];
@@ -262,25 +261,21 @@ __device__ __forceinline__ void fdsa_bin3(float2 q, float2 k, float2 v, float2& 
 // 240 shuffles - and the role lanes read their output spectrum back for the inverse transform.
 __global__ void __launch_bounds__(128, FDSA_MIN_BLOCKS) k_fdsa_patch_dw(const float* __restrict__ hid, const float* __restrict__ wdw,
                                                        const float* __restrict__ wfft, float* __restrict__ out, float* __restrict__ vv,
-                                                       int E, int H, int W, long long nitems) {
+                                                       int E, int H, int W, int per_plane) {
     __shared__ __align__(16) float s_x[4 * 8 * FDSA_IW];
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int t = lane >> 2, role = lane & 3;
-    const long long item = warp * 8 + t;
-    const bool valid = item < nitems;
-    const int pw = W >> 3, ph = H >> 3;
+    // grid.y = (image, channel e): uniform over the CTA; grid.x walks the patches of the plane, 32 per CTA
+    const int item = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 8 + t;
+    const bool valid = item < per_plane;
+    const int pw = W >> 3;
+    const int e = blockIdx.y % E;
+    const size_t b = blockIdx.y / E;
     float2* sx = reinterpret_cast<float2*>(s_x + ((threadIdx.x >> 5) * 8 + t) * FDSA_IW);
     float p[64];
     size_t off_out = 0;
-    int e = 0;
     if (valid) {
-        int px = (int)(item % pw);
-        long long r = item / pw;
-        int py = (int)(r % ph);
-        r /= ph;
-        e = (int)(r % E);
-        long long b = r / E;
+        const int px = item % pw, py = item / pw;
         const int ch = role * E + e;
         dw3_patch(hid + ((size_t)b * 4 * E + ch) * H * W, wdw + ch * 9, H, W, py * 8, px * 8, p);
         const size_t sp = (size_t)(py * 8) * W + px * 8;
@@ -464,9 +459,9 @@ FDN_API int fdn_fdsa_patch_dw(const float* hid, const float* wdw, const float* w
     FDN_REQUIRE(hid && wdw && wfft && out && vv && B > 0 && E > 0, "bad arguments");
     FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
     FDN_REQUIRE(fdn_aligned16(hid) && fdn_aligned16(out) && fdn_aligned16(vv), "pointers must be 16-byte aligned");
-    long long n = (long long)B * E * (H / 8) * (W / 8);
-    long long warps = (n + 7) / 8;
-    FDN_LAUNCH(k_fdsa_patch_dw, dim3(fdn_cdiv(warps, 4)), dim3(128), 0, st, hid, wdw, wfft, out, vv, E, H, W, n);
+    FDN_REQUIRE((long long)B * E <= 65535, "too many planes for one launch");
+    const int n = (H / 8) * (W / 8);
+    FDN_LAUNCH(k_fdsa_patch_dw, dim3(fdn_cdiv(n, 32), B * E), dim3(128), 0, st, hid, wdw, wfft, out, vv, E, H, W, n);
     return fdn_check_launch("k_fdsa_patch_dw");
 }
 
@@ -495,8 +490,9 @@ FDN_API int fdn_fdffn_patch_dw(const float* h, const float* s1, const float* wb,
     FDN_REQUIRE(h && s1 && wb && wspec && out && B > 0 && C > 0, "bad arguments");
     FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
     FDN_REQUIRE(fdn_aligned16(h) && fdn_aligned16(s1) && fdn_aligned16(out), "pointers must be 16-byte aligned");
-    long long n = (long long)B * C * (H / 8) * (W / 8);
-    FDN_LAUNCH_SEQ(k_fdffn_patch_dw, dim3(fdn_cdiv(n, 128)), dim3(128), 0, st, h, s1, wb, reinterpret_cast<const float2*>(wspec), out, C,
+    FDN_REQUIRE((long long)B * C <= 65535, "too many planes for one launch");
+    const int n = (H / 8) * (W / 8);
+    FDN_LAUNCH_SEQ(k_fdffn_patch_dw, dim3(fdn_cdiv(n, 128), B * C), dim3(128), 0, st, h, s1, wb, reinterpret_cast<const float2*>(wspec), out, C,
                    H, W, n);
     return fdn_check_launch("k_fdffn_patch_dw");
 }
