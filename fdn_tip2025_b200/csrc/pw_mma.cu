@@ -94,10 +94,10 @@ struct PwMmaParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Round to tf32 (10 explicit mantissa bits), nearest with ties away from zero - what cvt.rna.tf32.f32 computes for finite inputs.
+// ptxas expands that instruction into four (add, Inf/NaN test, select, mask); activations are finite, so two suffice.
 __device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                                 }
                                 if (!ok) x = 0.f;
                                 hi[j] = to_tf32(x);
-                                lo[j] = to_tf32(x - hi[j]);
+                                lo[j] = x - hi[j];      // exact; the tensor core reads only the tf32 bits of it (truncation: 2^-21 |x|, the size of the dropped lo*lo term)
                             }
                             *reinterpret_cast<float4*>(stage + soff[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                             if (PASSES == 3) *reinterpret_cast<float4*>(stage + a_bytes + soff[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
