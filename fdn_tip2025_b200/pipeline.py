@@ -21,10 +21,10 @@ def padded_size(h, w, multiple=32):
 
 
 class InferencePipeline:
-    def __init__(self, net, net_ipred, variant="lolblur"):
+    def __init__(self, net, net_ipred, variant="lolblur", use_graphs=False):
         if variant not in ("lolblur", "lolv1"):
             raise ValueError("variant must be 'lolblur' or 'lolv1'")
-        self.net, self.net_ipred, self.variant = net, net_ipred, variant
+        self.net, self.net_ipred, self.variant, self.use_graphs = net, net_ipred, variant, use_graphs
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("the pipeline runs on a CUDA device; there is no CPU path")
@@ -48,6 +48,41 @@ class InferencePipeline:
         ops.post_u8hwc(restored, out)
         return out, ratio
 
+    # ---- CUDA-graph replay -------------------------------------------------------------------
+    # A forward is ~750 kernel launches; for small frames (256x256, 400x600) the host cannot issue them as fast as the GPU
+    # retires them.  Per frame shape the whole device-side sequence (pre -> LPNet -> FDN -> post) is captured once into a CUDA
+    # graph with static uint8 input / output buffers and replayed afterwards: one launch per frame.
+    def _graph_for(self, b, h, w):
+        key = (b, h, w)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(key)
+        if entry is None:
+            frames = torch.zeros(b, h, w, 3, dtype=torch.uint8, device=self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):               # warm-up outside capture: twiddle tables, packed weights, kernel attributes
+                for _ in range(2):
+                    self.run_device(frames)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="relaxed"):    # kernel-attribute calls of the C ABI are not stream work
+                out, ratio = self.run_device(frames)
+            entry = (graph, frames, out, ratio)
+            self._graphs[key] = entry
+        return entry
+
+    @torch.no_grad()
+    def run_device_graphed(self, frames_u8):
+        """Same contract as run_device, replaying a CUDA graph captured for this (B, h, w).  The returned tensors are the graph's
+        static buffers: consume (or copy) them before the next call with the same shape."""
+        b, h, w, _ = frames_u8.shape
+        graph, frames, out, ratio = self._graph_for(b, h, w)
+        frames.copy_(frames_u8, non_blocking=True)
+        graph.replay()
+        return out, ratio
+
     def __call__(self, img_bgr_u8):
         """numpy uint8 [h,w,3] (or [B,h,w,3]) BGR as cv2.imread returns it -> restored frame(s), same layout."""
         a = np.ascontiguousarray(img_bgr_u8)
@@ -55,6 +90,6 @@ class InferencePipeline:
             raise RuntimeError("expected the uint8 array cv2.imread returns")
         single = a.ndim == 3
         t = torch.from_numpy(a[None] if single else a).pin_memory().to(self.device, non_blocking=True)
-        out, _ = self.run_device(t)
+        out, _ = self.run_device_graphed(t) if self.use_graphs else self.run_device(t)
         res = out.cpu().numpy()
         return res[0] if single else res

@@ -227,3 +227,19 @@ def test_inference_pipeline_matches_script_semantics(cuda_dev, variant, kind):
     ref = P.script_post(P.O.fdn(x64, r64, P._sd64(sd), variant)[0], h, w)[0]
     d = (got.int() - ref.int()).abs()
     assert d.max().item() <= 1 and (d > 0).float().mean().item() <= 1e-2
+
+
+def test_inference_pipeline_cuda_graph_replay(cuda_dev):
+    """CUDA-graph replay of the device-side sequence is bit-identical to the eager launches, also on the second frame."""
+    from fdn_tip2025_b200 import archs, pipeline, synth
+    net = archs.FDN()
+    net.load_state_dict(synth.fdn_state_dict(dim=32, seed=4, damp=0.005), strict=True)
+    net = net.to(cuda_dev).eval()
+    lp = archs.I_predict_net()
+    lp.load_state_dict(synth.lpnet_state_dict(seed=3), strict=True)
+    lp = lp.to(cuda_dev).eval()
+    eager = pipeline.InferencePipeline(net, lp, "lolblur")
+    graphed = pipeline.InferencePipeline(net, lp, "lolblur", use_graphs=True)
+    for i in range(3):
+        img = (synth.low_light_images(1, 50, 70, first_index=i)[0].permute(1, 2, 0) * 255).round().to(torch.uint8).flip(-1).contiguous().numpy()
+        assert (eager(img) == graphed(img)).all()
