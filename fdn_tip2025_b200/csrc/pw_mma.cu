@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(s_bet + MMA_MAX_K);
     uint64_t* raw_empty = raw_full + MMA_MAX_RING;
     uint64_t* a_full = raw_empty + MMA_MAX_RING;
-    uint64_t* a_empty = a_full + 2;
-    uint64_t* acc_full = a_empty + 2;        // [2]
+    uint64_t* a_empty = a_full + 4;          // [4] operand stages
+    uint64_t* acc_full = a_empty + 4;        // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const int gsize = PRO == 2 ? q.E : q.K;
 
     if (tid == 0) {
-        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS); }
-        for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS + (q.b_resident ? 0 : 1)); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS); }
+        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS / 32); }
+        for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS / 32 + (q.b_resident ? 0 : 1)); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_MMA_WARP) {
@@ -277,9 +277,23 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     }
     if (PRO != 0)
         for (int i = tid; i < MMA_MAX_K; i += MMA_THREADS) {
-            s_gam[i] = i < q.Kreal ? q.ln_w[i] : 0.f;
-            s_bet[i] = i < q.Kreal ? q.ln_b[i] : 0.f;
+            // gamma / beta in the order of the operand rows, zero on padding rows.  Prologue 2: row kk = g*10 + el of K block kb is
+            // channel g*E + kb*10 + el (grouped layout), so the producers read them with the same 128-bit loads as the plain order
+            int src = i;
+            bool ok = i < q.Kreal;
+            if (PRO == 2) {
+                const int kb = i >> 5, kk = i & 31, g = kk / MMA_EB, e = kb * MMA_EB + (kk - g * MMA_EB);
+                ok = g < 3 && e < q.E;
+                src = g * q.E + e;
+            }
+            s_gam[i] = ok ? q.ln_w[src] : 0.f;
+            s_bet[i] = ok ? q.ln_b[src] : 0.f;
         }
+    // The raw ring starts out as zeros: rows or pixels a tile does not load then hold zeros or stale (finite) activations, never the
+    // bit patterns a previous kernel left behind, and their contribution is removed by the zero gamma / beta and zero weight padding -
+    // so the producers need no per-element validity select.
+    for (int i = tid; i < (int)(q.ring * slot_bytes / 16); i += MMA_THREADS) reinterpret_cast<float4*>(s_raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (q.b_resident) {      // the whole weight chunk stays in shared memory for the lifetime of the CTA
         const float4* src = reinterpret_cast<const float4*>(bsrc);
         float4* dst = reinterpret_cast<float4*>(s_bres);
@@ -417,7 +431,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         for (int i = 0; i < 4; ++i) soff[i] = sw128_off(pix, half + 2 * i);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
-            const bool pvalid = p0 + pix < HW;
             float mu = 0.f, rs = 1.f;
             float gmu0 = 0.f, gmu1 = 0.f, gmu2 = 0.f, grs0 = 1.f, grs1 = 1.f, grs2 = 1.f;
             if (PRO == 1 || PRO == 3) {
@@ -463,7 +476,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 }
                 const int s = it % q.nstage;
                 unsigned char* stage = s_stage + s * stage_bytes;
-                const int kleft = q.K - kb * MMA_KB;                      // valid channels in this block (may exceed 32)
                 const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
                 if (it >= (uint32_t)q.nstage) mbar_wait_t(&a_empty[s], ((it / q.nstage) - 1) & 1, &w1, rec);
                 // The conversion is specialised on this thread's half (0/1) so that every per-element index (channel, LayerNorm
@@ -472,17 +484,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     constexpr int HALF = decltype(half_c)::value;
                     const float* gam_kb = s_gam + kb * MMA_KB;
                     const float* bet_kb = s_bet + kb * MMA_KB;
-                    const int e0 = kb * MMA_EB;                     // prologue 2: first channel (within a group) of this block
-                    const float* gam_g = s_gam + e0;
-                    const float* bet_g = s_bet + e0;
-                    const int E = q.E;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = HALF + 2 * i;
                         if (c < nchunks_used) {
                             float hi[4], lo[4];
                             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
-                            if (PRO == 1 || PRO == 3) {
+                            if (PRO != 0) {
                                 g4 = *reinterpret_cast<const float4*>(gam_kb + 4 * c);
                                 b4 = *reinterpret_cast<const float4*>(bet_kb + 4 * c);
                             }
@@ -491,23 +499,21 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                             for (int j = 0; j < 4; ++j) {
                                 const int kk = 4 * c + j;
                                 float x = raw[kk * MMA_TP];
-                                bool ok = pvalid && kk < kleft;
                                 if (PRO == 1) {
                                     x = (x - mu) * rs * gj[j] + bj[j];
                                 } else if (PRO == 2) {
                                     // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el
                                     const int g = kk / MMA_EB, el = kk - g * MMA_EB;
-                                    ok = pvalid && g < 3 && e0 + el < E;
                                     if (g < 3) {
                                         const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
-                                        // gamma/beta reads past E stay inside the (zero padded) table and are discarded by ok
-                                        x = ((x - gm) * gr * gam_g[g * E + el] + bet_g[g * E + el]) * raw[MMA_P2_V_OFF / 4 + el * MMA_TP];
+                                        x = ((x - gm) * gr * gj[j] + bj[j]) * raw[MMA_P2_V_OFF / 4 + el * MMA_TP];
+                                    } else {
+                                        x = 0.f;          // rows 30, 31 of a grouped block
                                     }
                                 } else if (PRO == 3) {
                                     const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
                                     x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
                                 }
-                                if (!ok) x = 0.f;
                                 hi[j] = to_tf32(x);
                                 lo[j] = x - hi[j];      // exact; the tensor core reads only the tf32 bits of it (truncation: 2^-21 |x|, the size of the dropped lo*lo term)
                             }
@@ -517,9 +523,15 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     }
                 };
                 if (half == 0) convert(std::integral_constant<int, 0>{}); else convert(std::integral_constant<int, 1>{});
-                mbar_arrive(&raw_empty[r]);            // this thread is done with the raw slot
+                // One arrival per warp, not per thread: 256 arrivals on one shared-memory word serialise (two barriers per K block),
+                // which was a fixed ~2 k cycles per K block.  Every lane makes its operand stores visible to the async proxy, the
+                // warp converges, lane 0 signals both barriers.
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&a_full[s]);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&raw_empty[r]);        // the warp is done with the raw slot
+                    mbar_arrive(&a_full[s]);
+                }
             }
         }
     } else if (warp == MMA_MMA_WARP) {
@@ -626,7 +638,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 }
                 if (c16 == c16_end - 1) {        // this warp's TMEM reads of the tile are complete: hand the accumulators back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[buf]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 const int n0 = chunk * q.Nc + c16 * 16;
                 if (valid) {
@@ -652,7 +665,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             }
             if (c16_begin >= c16_end) {          // a warp without columns (Nc == 16) still takes part in the hand-back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&acc_empty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
         }
     }
@@ -693,13 +707,15 @@ struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
     const size_t slot = prologue == 2 ? (size_t)MMA_P2_SLOT : (size_t)MMA_SLOT_BYTES * (prologue == 3 ? 2 : 1);
-    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 8) * sizeof(uint64_t) + 64;
+    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 12) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
     const int ring_min = (prologue == 1 || prologue == 3) ? max(nkb, 2) : 2;  // LN needs all K blocks of a tile resident
     PwMmaPlan best;
     bool found = false;
+    int ns_hi = 2, ns_lo = 1;                 // operand stages; FDN_MMA_NSTAGE pins the count (dev knob, up to 4)
+    if (const char* e = getenv("FDN_MMA_NSTAGE")) { ns_hi = ns_lo = max(1, min(4, atoi(e))); }
     for (int resident = 1; resident >= 0; --resident)
-        for (int nstage = 2; nstage >= 1; --nstage) {
+        for (int nstage = ns_hi; nstage >= ns_lo; --nstage) {
             const size_t fixed = misc + (resident ? (size_t)nkb * 2 * b_bytes : 0) + nstage * (2 * a_bytes + (resident ? 0 : 2 * b_bytes));
             if (fixed + ring_min * slot > budget) continue;
             int ring = (int)((budget - fixed) / slot);
