@@ -40,9 +40,9 @@
 #define MMA_EPI_WARP0 8
 #define MMA_EPI_THREADS 256
 #define MMA_MMA_WARP 16
-#define MMA_LOAD_WARP0 17     // two loader warps (19 warps -> 104 registers per thread; a third loader warp caps them at 96 and spills)
-#define MMA_LOAD_THREADS 64
-#define MMA_THREADS 608
+#define MMA_LOAD_WARP0 17     // three loader warps: a warp retires its lanes' bulk copies one after another (~60 cycles each), so the copy issue rate scales with the number of loader warps; 20 warps still get 96 registers each (a 21st caps them at 80 and spills)
+#define MMA_LOAD_THREADS 96
+#define MMA_THREADS 640
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
@@ -334,7 +334,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         } else if (q.bulk) {
             // one TMA bulk copy (512 contiguous bytes) per channel row.  Issuing a bulk copy costs ~60 cycles of one thread's
             // uniform datapath, so the rows of every K block are interleaved over all loader warps that do not stream weights.
-            const int nlw = q.b_resident ? MMA_LOAD_THREADS / 32 : MMA_LOAD_THREADS / 32 - 1;
+            // activation loader warps: two (a compile-time constant) except for the gate prologue with resident weights, whose 46 rows per
+            // K block use all three; with streamed weights the last loader warp carries the weight panels
+            const int nlw = PRO == 2 ? (q.b_resident ? MMA_LOAD_THREADS / 32 : MMA_LOAD_THREADS / 32 - 1) : 2;
             const int lw = warp - MMA_LOAD_WARP0;
             if (lw < nlw)
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
