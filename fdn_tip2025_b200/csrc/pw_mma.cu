@@ -6,12 +6,12 @@
 // FDSA to_hidden / project_out, FDFFN project_in / project_out, FCAFFN project_in / project_out, Fuse conv / conv2
 // (FDN_arch.py:388-389, 451-452, 562, 566, 685-686).
 //
-// Persistent, warp-specialised kernel (19 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
-//   warps 17-18 loaders: stream raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
+// Persistent, warp-specialised kernel (20 warps per CTA, one CTA per SM, static round-robin over pixel tiles):
+//   warps 17-19 loaders: stream raw [32 channels][128 pixels] blocks of X (and of the per-pixel side operand) from HBM
 //               into a shared-memory ring, one TMA bulk copy (cp.async.bulk, 512 contiguous bytes) per channel row with
 //               completion counted on the slot's mbarrier - several K blocks ahead of the consumers, which keeps enough
 //               bytes in flight to cover HBM latency.  Issuing a bulk copy costs ~60 cycles of the issuing thread, so the
-//               rows are interleaved over the lanes of both warps.  When the weights do not fit in shared memory the last
+//               rows are interleaved over the lanes of the loader warps.  When the weights do not fit in shared memory the last
 //               loader warp streams one weight panel per K block instead.  (FDN_MMA_BULK=0 selects 16-byte cp.async.)
 //   warps 0-7   producers: two threads per pixel; take the LayerNorm statistics from shared memory (two-pass mean /
 //               biased variance like the reference), apply the per-pixel prologue, split each value into tf32 hi + lo
