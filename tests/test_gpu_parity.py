@@ -243,3 +243,20 @@ def test_inference_pipeline_cuda_graph_replay(cuda_dev):
     for i in range(3):
         img = (synth.low_light_images(1, 50, 70, first_index=i)[0].permute(1, 2, 0) * 255).round().to(torch.uint8).flip(-1).contiguous().numpy()
         assert (eager(img) == graphed(img)).all()
+
+
+def test_micro_batching_is_exact(cuda_dev, monkeypatch):
+    """A batch processed in micro-batches (FDN_B200_MICRO_BATCH) gives bit-identical images to one image at a time: no op mixes images."""
+    from fdn_tip2025_b200 import archs, synth
+    net = archs.FDN()
+    net.load_state_dict(synth.fdn_state_dict(dim=32, seed=5, damp=0.005), strict=True)
+    net = net.to(cuda_dev).eval()
+    x = synth.low_light_images(3, 64, 96).to(cuda_dev)
+    ratio = torch.tensor([[0.3], [0.35], [0.4]], device=cuda_dev)
+    monkeypatch.setenv("FDN_B200_MICRO_BATCH", "2")
+    whole = net(x, ratio_i=ratio)
+    monkeypatch.setenv("FDN_B200_MICRO_BATCH", "1")
+    for i in range(3):
+        one = net(x[i:i + 1], ratio_i=ratio[i:i + 1])
+        for a, b in zip(whole, one):
+            assert torch.equal(a[i:i + 1], b)
