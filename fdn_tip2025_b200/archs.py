@@ -250,9 +250,12 @@ def _fdsa(cx, x, p):
     if mode == "ffma":
         ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=e * h * w)
         ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
-    else:   # norm1..3, the v_value gate and project_out in one kernel (LayerNorm statistics from a small pre-pass)
-        stats = _new(x, b, 3, 2, h * w)
-        ops.group_stats(o, stats, 3)
+    else:   # norm1..3, the v_value gate and project_out in one kernel.  LayerNorm statistics: computed by the kernel's producers when
+        # all K blocks of a pixel tile fit its shared-memory ring (E <= 40, i.e. level 1), else from a small pre-pass
+        stats = None
+        if e > 40 or os.environ.get("FDN_B200_GATE_STATS") == "prepass":
+            stats = _new(x, b, 3, 2, h * w)
+            ops.group_stats(o, stats, 3)
         ops.pw_mma([o], cx.packed_grouped(p + "attn.project_out.weight", e), out, prologue=2, ln=(g3, b3), aux=vv, aux_bs=e * h * w,
                    stats=stats, res=x, res_coef=1.0, passes=1 if mode == "tf32" else 3)
     return out

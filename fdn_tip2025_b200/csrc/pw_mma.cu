@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     unsigned char* s_stage = s_bres + bres_bytes;
     unsigned char* s_raw = s_stage + q.nstage * stage_bytes;
     float* s_part = reinterpret_cast<float*>(s_raw + q.ring * slot_bytes);       // [2][128] partial sums
-    float* s_gam = s_part + 2 * MMA_TP;                                          // [MMA_MAX_K] LayerNorm gamma
+    float* s_gam = s_part + 6 * MMA_TP;                                          // [MMA_MAX_K] LayerNorm gamma   (s_part: [2 halves][3 groups][128])
     float* s_bet = s_gam + MMA_MAX_K;                                            // [MMA_MAX_K] LayerNorm beta
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(s_bet + MMA_MAX_K);
     uint64_t* raw_empty = raw_full + MMA_MAX_RING;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                             // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once;
                             // virtual rows 0..29 x, 30..39 v_value, 40..45 the LayerNorm statistics (first K block only)
                             const int ne = min(MMA_EB, q.E - kb * MMA_EB);
-                            if (lw == 0 && lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)(4 * ne + (kb == 0 ? 6 : 0)) * len);
+                            if (lw == 0 && lane == 0) mbar_expect_tx(&raw_full[r], (uint32_t)(4 * ne + (kb == 0 && q.stats ? 6 : 0)) * len);
                             for (int vi = lane * nlw + lw; vi < 4 * MMA_EB + 6; vi += 32 * nlw) {      // virtual rows of this lane
                                 const int g = vi / MMA_EB, el = vi - g * MMA_EB;
                                 if (g < 3) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                                 } else if (g == 3) {
                                     if (el < ne)
                                         bulk_g2s(slot + MMA_P2_V_OFF + el * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(kb * MMA_EB + el) * HW + p0, len, &raw_full[r]);
-                                } else if (kb == 0) {
+                                } else if (kb == 0 && q.stats) {
                                     const int sr = vi - 4 * MMA_EB;
                                     bulk_g2s(slot + MMA_P2_ST_OFF + sr * (MMA_TP * 4), q.stats + ((size_t)b * 6 + sr) * HW + p0, len, &raw_full[r]);
                                 }
@@ -467,11 +467,55 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 prod_sync();
                 rs = 1.0f / sqrtf((s_part[pix] + s_part[MMA_TP + pix]) / (float)q.K + 1e-5f);
             }
+            if (PRO == 2 && q.stats == nullptr) {
+                // LayerNorm statistics of the three groups from the raw ring (all K blocks of the tile are resident: the host only
+                // selects this mode when they fit) - two passes like k_group_stats, which this replaces for small E
+                auto group_pass = [&](auto half_c, float m0, float m1, float m2, bool second, float (&acc)[3]) {
+                    constexpr int HALF = decltype(half_c)::value;
+                    acc[0] = acc[1] = acc[2] = 0.f;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (!second) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
+                        const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                        const int ne = min(MMA_EB, q.E - kb * MMA_EB);
+#pragma unroll
+                        for (int kk2 = 0; kk2 < 15; ++kk2) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const int kk = 2 * kk2 + HALF;              // rows 0..29: group kk / 10, channel kk % 10 of this block
+                            const int g = kk / MMA_EB, el = kk - g * MMA_EB;
+                            if (el < ne) {
+                                const float x = raw[kk * MMA_TP];
+                                if (!second) acc[g] += x;
+                                else { const float d = x - (g == 0 ? m0 : (g == 1 ? m1 : m2)); acc[g] += d * d; }
+                            }
+                        }
+                    }
+                };
+                float acc[3];
+                if (half == 0) group_pass(std::integral_constant<int, 0>{}, 0.f, 0.f, 0.f, false, acc);
+                else group_pass(std::integral_constant<int, 1>{}, 0.f, 0.f, 0.f, false, acc);
+                prod_sync();                       // the previous tile's readers of s_part are done
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s_part[(half * 3 + g) * MMA_TP + pix] = acc[g];
+                prod_sync();
+                const float invE = 1.0f / (float)q.E;
+                gmu0 = (s_part[0 * MMA_TP + pix] + s_part[3 * MMA_TP + pix]) * invE;
+                gmu1 = (s_part[1 * MMA_TP + pix] + s_part[4 * MMA_TP + pix]) * invE;
+                gmu2 = (s_part[2 * MMA_TP + pix] + s_part[5 * MMA_TP + pix]) * invE;
+                if (half == 0) group_pass(std::integral_constant<int, 0>{}, gmu0, gmu1, gmu2, true, acc);
+                else group_pass(std::integral_constant<int, 1>{}, gmu0, gmu1, gmu2, true, acc);
+                prod_sync();
+#pragma unroll
+                for (int g = 0; g < 3; ++g) s_part[(half * 3 + g) * MMA_TP + pix] = acc[g];
+                prod_sync();
+                grs0 = 1.0f / sqrtf((s_part[0 * MMA_TP + pix] + s_part[3 * MMA_TP + pix]) * invE + 1e-5f);
+                grs1 = 1.0f / sqrtf((s_part[1 * MMA_TP + pix] + s_part[4 * MMA_TP + pix]) * invE + 1e-5f);
+                grs2 = 1.0f / sqrtf((s_part[2 * MMA_TP + pix] + s_part[5 * MMA_TP + pix]) * invE + 1e-5f);
+            }
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int r = it % q.ring;
                 const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
                 mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
-                if (PRO == 2 && kb == 0) {
+                if (PRO == 2 && kb == 0 && q.stats != nullptr) {
                     const float* st = raw + MMA_P2_ST_OFF / 4;
                     gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
                     gmu2 = st[4 * MMA_TP]; grs2 = st[5 * MMA_TP];
@@ -706,12 +750,12 @@ __global__ void __launch_bounds__(256) k_group_stats(const float* __restrict__ x
 
 struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 
-static bool pw_mma_plan(int Nc, int nkb, int prologue, PwMmaPlan* out) {
+static bool pw_mma_plan(int Nc, int nkb, int prologue, bool ring_holds_tile, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
     const size_t slot = prologue == 2 ? (size_t)MMA_P2_SLOT : (size_t)MMA_SLOT_BYTES * (prologue == 3 ? 2 : 1);
-    const size_t misc = 1024 + (2 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 12) * sizeof(uint64_t) + 64;
+    const size_t misc = 1024 + (6 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 12) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
-    const int ring_min = (prologue == 1 || prologue == 3) ? max(nkb, 2) : 2;  // LN needs all K blocks of a tile resident
+    const int ring_min = ring_holds_tile ? max(nkb, 2) : 2;  // LayerNorm statistics need all K blocks of a tile resident
     PwMmaPlan best;
     bool found = false;
     int ns_hi = 2, ns_lo = 1;                 // operand stages; FDN_MMA_NSTAGE pins the count (dev knob, up to 4)
@@ -770,7 +814,7 @@ FDN_API int fdn_group_stats(const float* x, float* stats, int B, int G, int C, i
 // Tensor-core 1x1 convolution.  bpack is the host-packed weight (see fdn_tip2025_b200/packing.py): for every output chunk of
 // Nc (multiple of 16, <= 256) channels and every block of 32 input channels, a [Nc][32] tf32-hi panel followed by the tf32-lo
 // panel, both in the K-major SWIZZLE_128B image.  nchunks*Nc >= N.  prologue: 0 none, 1 LayerNorm over the K inputs,
-// 2 FDSA gate (three LayerNorm groups of K/3 channels with precomputed `stats`, times v_value = aux), 3 FCAFFN mix
+// 2 FDSA gate (three LayerNorm groups of K/3 channels - statistics precomputed in `stats`, or NULL: computed here, K/3 <= 40 - times v_value = aux), 3 FCAFFN mix
 // LN(src)*aux + aux.  passes: 3 = 3xTF32 (fp32-level accuracy), 1 = single TF32.  HW must be a multiple of 4.
 FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, const float* bpack, int N, int Nc, int nchunks,
                        int prologue, const float* ln_w, const float* ln_b, const float* aux, long long aux_bs, const float* stats,
@@ -787,7 +831,7 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     FDN_REQUIRE(HW % 4 == 0, "HW must be a multiple of 4 (16-byte bulk copies)");
     if (prologue) FDN_REQUIRE(ln_w && ln_b && !src1, "LayerNorm prologue needs gamma/beta and a single source");
     if (prologue >= 2) FDN_REQUIRE(aux != nullptr && fdn_aligned16(aux) && aux_bs % 4 == 0, "prologue needs a 16-byte aligned aux tensor");
-    if (prologue == 2) FDN_REQUIRE(c0 % 3 == 0 && stats && fdn_aligned16(stats), "FDSA gate needs 3 equal groups and their statistics");
+    if (prologue == 2) FDN_REQUIRE(c0 % 3 == 0 && (!stats || fdn_aligned16(stats)), "FDSA gate needs 3 equal groups (statistics: precomputed, or NULL = in the kernel)");
     FDN_REQUIRE(fdn_aligned16(bpack) && fdn_aligned16(src0) && (!src1 || fdn_aligned16(src1)), "pointers must be 16-byte aligned");
     PwMmaParams q;
     q.src0 = src0; q.src1 = src1; q.C0 = c0; q.C1 = src1 ? c1 : 0;
@@ -809,7 +853,7 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
     PwMmaPlan plan;
-    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, &plan), "tile does not fit in shared memory");
+    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), &plan), "tile does not fit in shared memory");
     q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
     // accumulators: one K block (<= 12 accumulations) needs no split; longer K keeps hi*hi and the corrections apart and
     // spreads the K blocks over up to three main accumulators

@@ -99,7 +99,7 @@ int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1, int c1
  * N <= 256 output channels per chunk.  bpack is the weight packed by fdn_tip2025_b200/packing.py into the K-major
  * SWIZZLE_128B shared-memory image (tf32 hi panel + tf32 lo panel per 32-channel block).  prologue (applied per pixel while
  * the A operand is built): 0 none, 1 LayerNorm over the K inputs (FDN_arch.py:671,673), 2 FDSA gate = three LayerNorm groups
- * (statistics from fdn_group_stats) times v_value=aux (FDN_arch.py:633-639), 3 FCAFFN mix LN(src)*aux + aux (FDN_arch.py:420).  Epilogue: +bias,
+ * (statistics = fdn_group_stats output, or NULL to have the kernel compute them - allowed while K/3 <= 40) times v_value=aux (FDN_arch.py:633-639), 3 FCAFFN mix LN(src)*aux + aux (FDN_arch.py:420).  Epilogue: +bias,
  * *film_mul+film_add, +res_coef*res.  passes: 3 = 3xTF32 split (fp32-level accuracy), 1 = single TF32. */
 int fdn_has_tcgen05(void);
 /* Development aid: 8 uint64 device counters receiving the per-role barrier wait cycles of following fdn_pw_mma launches (NULL = off).
