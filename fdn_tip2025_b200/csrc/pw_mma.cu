@@ -14,14 +14,16 @@
 //               rows are interleaved over the lanes of the loader warps.  When the weights do not fit in shared memory the last
 //               loader warp streams one weight panel per K block instead.  (FDN_MMA_BULK=0 selects 16-byte cp.async.)
 //   warps 0-7   producers: two threads per pixel; take the LayerNorm statistics from shared memory (two-pass mean /
-//               biased variance like the reference), apply the per-pixel prologue, split each value into tf32 hi + lo
-//               and store it into the canonical K-major SWIZZLE_128B operand stage
+//               biased variance like the reference; for the gate prologue with E <= 40 also the three group statistics), apply
+//               the per-pixel prologue, split each value into tf32 hi + lo (lo is left untruncated: the tensor core reads only its
+//               tf32 bits) and store it into the canonical K-major SWIZZLE_128B operand stage.  No per-element validity select:
+//               the raw ring starts as zeros and gamma / beta / weights are zero on padding rows
 //   warp  16    MMA issuer: one elected lane issues tcgen05.mma (cta_group::1, kind::tf32, 128 x N x 8) with the weight
 //               panel that is resident in shared memory (packed on the host into the UMMA image) and owns TMEM
 //   warps 8-15  epilogue: thread = TMEM lane = pixel (two warps per lane quadrant split the columns); residual prefetched into registers, tcgen05.ld, IEEE sum of the
 //               accumulators, bias / FiLM / residual, 128-byte coalesced NCHW stores
-// Barriers: raw_full[r] (tx bytes) -> producers -> raw_empty[r]; a_full[s] (256 arrivals) -> MMA; tcgen05.commit ->
-// a_empty[s]; commit -> acc_full -> epilogue -> acc_empty (256 arrivals) -> MMA of the next tile.
+// Barriers: raw_full[r] (tx bytes) -> producers -> raw_empty[r]; a_full[s] (one arrival per producer warp) -> MMA; tcgen05.commit ->
+// a_empty[s]; commit -> acc_full -> epilogue -> acc_empty (one arrival per epilogue warp) -> MMA of the next tile.
 //
 // Precision: passes = 3 ("3xTF32", default) splits both operands into tf32 hi + tf32 lo and accumulates
 // hi*hi + hi*lo + lo*hi.  The split itself is exact to 7e-8; because the tensor core truncates its fp32 accumulator after
