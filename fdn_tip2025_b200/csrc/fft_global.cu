@@ -480,11 +480,21 @@ struct SpecMlpParams {
     const float* w;           // packed: W1m[NC*NC] b1m[NC] W2m[NC*NC] b2m[NC] W1p b1p W2p b2p   (row-major [out][in])
 };
 
-// y[n] = b[n] + sum_k W[n][k] x[k] with the weight row read as 128-bit broadcasts (4 FMAs per shared-memory load)
+// A CTA of 128 threads owns 32 consecutive bins of one image: lane = bin, warp q computes output channels [q*NC/4, (q+1)*NC/4) of every
+// layer, so a weight row is a warp-wide broadcast and the layer inputs (staged in shared memory as [channel][bin]) are read
+// conflict free into registers once per layer.  The four NC x NC layers are 4 * NC/4 * NC FMAs per thread instead of 4 * NC * NC in a
+// single thread with all channels in registers (255 registers and spills at NC = 48).
+#define SM_BINS 32
 template <int NC>
-__device__ __forceinline__ void mlp_layer(const float* __restrict__ W, const float* __restrict__ b, const float (&x)[NC], float (&y)[NC]) {
+__device__ __forceinline__ void mlp_layer_q(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ xin, int bin, int q,
+                                            float (&y)[NC / 4]) {
+    constexpr int NO = NC / 4;
+    float x[NC];
 #pragma unroll
-    for (int n = 0; n < NC; ++n) {
+    for (int k = 0; k < NC; ++k) x[k] = xin[k * SM_BINS + bin];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        const int n = q * NO + o;
         float acc = b[n];
         const float4* w4 = reinterpret_cast<const float4*>(W + n * NC);
 #pragma unroll
@@ -495,16 +505,20 @@ __device__ __forceinline__ void mlp_layer(const float* __restrict__ W, const flo
             acc += w.z * x[4 * k + 2];
             acc += w.w * x[4 * k + 3];
         }
-        y[n] = acc;
+        y[o] = acc;
     }
 }
 
 template <int NC>
 __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
-    static_assert(NC % 4 == 0, "rows are read as float4");
-    __shared__ __align__(16) float sw[4 * (NC * NC + NC)];
-    for (int i = threadIdx.x; i < 4 * (NC * NC + NC); i += blockDim.x) sw[i] = q.w[i];
-    __syncthreads();
+    static_assert(NC % 16 == 0 || NC == 12 || NC == 24, "NC/4 outputs per warp, rows read as float4");
+    constexpr int NO = NC / 4;
+    FDN_DYN_SMEM(smem);
+    float* sw = reinterpret_cast<float*>(smem);                 // 4 * (NC*NC + NC) weights
+    float* xm = sw + 4 * (NC * NC + NC);                        // [NC][32] magnitudes, later the hidden layer
+    float* xp = xm + NC * SM_BINS;                              // [NC][32] phases
+    float* hd = xp + NC * SM_BINS;                              // [NC][32] hidden
+    for (int i = threadIdx.x; i < 4 * (NC * NC + NC); i += 128) sw[i] = q.w[i];
     const float* W1m = sw;
     const float* b1m = W1m + NC * NC;
     const float* W2m = b1m + NC;
@@ -513,36 +527,37 @@ __global__ void __launch_bounds__(128) k_spec_mlp(SpecMlpParams q) {
     const float* b1p = W1p + NC * NC;
     const float* W2p = b1p + NC;
     const float* b2p = W2p + NC * NC;
-    long long bin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int bimg = blockIdx.y;
-    if (bin >= q.nbins) return;
-    float2* z = q.spec + (size_t)bimg * NC * q.plane_stride + bin;
-    float in[NC], hid[NC], om[NC];
-    // magnitude path
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const long long bin = (long long)blockIdx.x * SM_BINS + lane;
+    const bool ok = bin < q.nbins;
+    float2* z = q.spec + (size_t)blockIdx.y * NC * q.plane_stride + (ok ? bin : 0);
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        float2 v = z[(size_t)c * q.plane_stride];
-        in[c] = sqrtf(v.x * v.x + v.y * v.y);
+    for (int o = 0; o < NO; ++o) {
+        const int c = wq * NO + o;
+        const float2 v = ok ? z[(size_t)c * q.plane_stride] : make_float2(1.f, 0.f);
+        xm[c * SM_BINS + lane] = sqrtf(v.x * v.x + v.y * v.y);
+        xp[c * SM_BINS + lane] = atan2f(v.y, v.x);
     }
-    mlp_layer<NC>(W1m, b1m, in, hid);
+    __syncthreads();
+    float t[NO], om[NO];
+    mlp_layer_q<NC>(W1m, b1m, xm, lane, wq, t);
 #pragma unroll
-    for (int n = 0; n < NC; ++n) hid[n] = fdn_lrelu(hid[n]);
-    mlp_layer<NC>(W2m, b2m, hid, om);
-    // phase path
+    for (int o = 0; o < NO; ++o) hd[(wq * NO + o) * SM_BINS + lane] = fdn_lrelu(t[o]);
+    __syncthreads();
+    mlp_layer_q<NC>(W2m, b2m, hd, lane, wq, om);
+    mlp_layer_q<NC>(W1p, b1p, xp, lane, wq, t);
+    __syncthreads();                                            // every warp is done reading hd
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        float2 v = z[(size_t)c * q.plane_stride];
-        in[c] = atan2f(v.y, v.x);
-    }
-    mlp_layer<NC>(W1p, b1p, in, hid);
+    for (int o = 0; o < NO; ++o) hd[(wq * NO + o) * SM_BINS + lane] = fdn_lrelu(t[o]);
+    __syncthreads();
+    mlp_layer_q<NC>(W2p, b2p, hd, lane, wq, t);
+    if (ok) {
 #pragma unroll
-    for (int n = 0; n < NC; ++n) hid[n] = fdn_lrelu(hid[n]);
-    mlp_layer<NC>(W2p, b2p, hid, in);
-#pragma unroll
-    for (int n = 0; n < NC; ++n) {
-        float sn, cs;
-        sincosf(in[n], &sn, &cs);
-        z[(size_t)n * q.plane_stride] = make_float2(om[n] * cs, om[n] * sn);
+        for (int o = 0; o < NO; ++o) {
+            float sn, cs;
+            sincosf(t[o], &sn, &cs);
+            z[(size_t)(wq * NO + o) * q.plane_stride] = make_float2(om[o] * cs, om[o] * sn);
+        }
     }
 }
 
@@ -683,10 +698,19 @@ FDN_API int fdn_spec_mlp(float* spec, long long plane_stride, long long nbins, i
     q.nbins = nbins;
     q.B = B;
     q.w = w;
-    dim3 grid(fdn_cdiv(nbins, 128), B), block(128);
-    if (NC == 12) { auto k = k_spec_mlp<12>; FDN_LAUNCH(k, grid, block, 0, st, q); }
-    else if (NC == 24) { auto k = k_spec_mlp<24>; FDN_LAUNCH(k, grid, block, 0, st, q); }
-    else if (NC == 48) { auto k = k_spec_mlp<48>; FDN_LAUNCH(k, grid, block, 0, st, q); }
+    dim3 grid(fdn_cdiv(nbins, SM_BINS), B), block(128);
+#define FDN_SPEC_MLP_CASE(NCV)                                                                         \
+    {                                                                                                  \
+        auto k = k_spec_mlp<NCV>;                                                                      \
+        const size_t smem = (size_t)(4 * (NCV * NCV + NCV) + 3 * NCV * SM_BINS) * sizeof(float);       \
+        int rc = set_smem(k, smem);                                                                    \
+        if (rc) return rc;                                                                             \
+        FDN_LAUNCH(k, grid, block, smem, st, q);                                                       \
+    }
+    if (NC == 12) FDN_SPEC_MLP_CASE(12)
+    else if (NC == 24) FDN_SPEC_MLP_CASE(24)
+    else if (NC == 48) FDN_SPEC_MLP_CASE(48)
     else FDN_REQUIRE(false, "unsupported channel count (12/24/48)");
+#undef FDN_SPEC_MLP_CASE
     return fdn_check_launch("k_spec_mlp");
 }
