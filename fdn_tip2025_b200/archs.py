@@ -9,6 +9,7 @@ libfdn_b200.so through ``ops`` (C ABI).  Inference only: no autograd, CUDA tenso
 Unlike the reference constructors (FDN_arch.py:860-862, fdnlol24_arch.py:972-974) nothing is torch.load-ed from a
 hard-coded path: ``net_a.*`` is filled by the full checkpoint like every other key.
 """
+import contextlib
 import os
 
 import torch
@@ -220,14 +221,23 @@ def _gemm_mode():
     if mode not in ("tf32x3", "tf32", "ffma"):
         raise RuntimeError("FDN_B200_GEMM must be tf32x3, tf32 or ffma")
     if mode != "ffma" and not ops.has_tcgen05():
-        return "ffma"
+        # never downgrade silently: the only library without the tensor-core kernel is the host emulation build of tests/emu
+        raise RuntimeError("FDN_B200_GEMM=%s needs the sm_100a build of libfdn_b200.so (tcgen05 kernels); set FDN_B200_GEMM=ffma "
+                           "explicitly to run the CUDA-core GEMM kernel" % mode)
     return mode
+
+
+MMA_MAX_K = 512      # csrc/pw_mma.cu: LayerNorm gamma/beta staging; wider layers (FDformer dim 48 at level 3) run on k_pw_conv
+
+
+def _mma_ok(k):
+    return k <= MMA_MAX_K
 
 
 def _conv1x1(cx, srcs, key, out, ln=None, bias=None, film=None, res=None):
     """1x1 convolution of the FDformer blocks: tcgen05 kernel, or the FFMA kernel when FDN_B200_GEMM=ffma."""
     mode = _gemm_mode()
-    if mode == "ffma":
+    if mode == "ffma" or not _mma_ok(sum(t.shape[1] for t in srcs)):
         ops.pw_conv([(t, 0) for t in srcs], cx.wt(key), out, bias=bias, ln=ln, film=film, res=res, res_coef=1.0)
     else:
         ops.pw_mma(srcs, cx.packed(key), out, prologue=1 if ln else 0, ln=ln, bias=bias, film=film, res=res, res_coef=1.0,
@@ -247,7 +257,7 @@ def _fdsa(cx, x, p):
     g3, b3 = cx.ln3(p + "attn.")
     out = _new(x, b, c, h, w)
     mode = _gemm_mode()
-    if mode == "ffma":
+    if mode == "ffma" or not _mma_ok(3 * e):
         ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=e * h * w)
         ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
     else:   # norm1..3, the v_value gate and project_out in one kernel.  LayerNorm statistics: computed by the kernel's producers when
@@ -305,7 +315,7 @@ def _fcaffn(cx, x, side, p):
     ops.film_maps(img, cx.film(p + "ffn2.", "mul"), cx.film(p + "ffn2.", "add"), fmul, fadd)
     t = _new(x, b, c, h, w)
     mode = _gemm_mode()
-    if mode == "ffma":
+    if mode == "ffma" or not _mma_ok(c):
         g, bt = cx.ln(p + "ffn2.norm.")
         ops.chan_ln(y, y, g, bt, mul=x1, mul_bs=c * h * w, add=x1, add_bs=c * h * w)
         ops.pw_conv([(y, 0)], cx.wt(p + "ffn2.project_in.weight"), t, film=(fmul, fadd))
@@ -343,7 +353,7 @@ def _fuse(cx, enc, dec, p):
     wt, bias = cx.fuse_out(p)
     out = _new(enc, b, n, h, w)
     mode = _gemm_mode()
-    if mode == "ffma":
+    if mode == "ffma" or not _mma_ok(2 * n):
         ops.pw_conv([(x, 0)], wt, out, bias=bias)
     else:
         ops.pw_mma([x], cx.packed_fuse_out(p), out, bias=bias, passes=1 if mode == "tf32" else 3)
@@ -550,6 +560,32 @@ def _fdn(cx, img, ratio, variant):
     return out, q1, q2, q3
 
 
+def _on_device(x):
+    """Make the tensor's GPU the current device for the launches below (streams, twiddle tables and function attributes of the
+    library are per device); CPU tensors only occur under the host emulation build of tests/emu."""
+    return torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext()
+
+
+def _flat_ratio(ratio, b, dev):
+    """[B,1] / [B,1,1,1] / scalar ratio -> flat [B] fp32 on the input's device (the reference broadcasts a single value)."""
+    r = ratio.detach().float().reshape(-1).to(dev)
+    if r.numel() == 1 and b > 1:
+        r = r.expand(b)
+    if r.numel() != b:
+        raise RuntimeError("ratio must hold one value per image (or a single value): got %d values for %d images" % (r.numel(), b))
+    return r.contiguous()
+
+
+def _side(t, name, shape, dev):
+    if t is None:
+        raise RuntimeError("%s is required" % name)
+    if not t.is_cuda or t.device != dev:
+        raise RuntimeError("%s must be on %s (got %s)" % (name, dev, t.device))
+    if tuple(t.shape) != tuple(shape):
+        raise RuntimeError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t.detach().float().contiguous()
+
+
 def _check_input(x, multiple):
     ops._device_ok(x)
     if x.dim() != 4 or x.shape[1] != 3:
@@ -585,15 +621,14 @@ class _FDNBase(_Net):
         x = _check_input(inp_img, 32)
         if ratio_i is None:
             raise RuntimeError("ratio_i ([B,1] tensor) is required")       # the reference dereferences None here too
-        ratio = ratio_i.detach().float().reshape(-1).contiguous().to(x.device)
-        if ratio.numel() != x.shape[0]:
-            raise RuntimeError("ratio_i must hold one value per image")
+        ratio = _flat_ratio(ratio_i, x.shape[0], x.device)
         cx = self._context()
         b, _, h, w = x.shape
         mb = _micro_batch(b, h, w)
         outs = []
-        for s in range(0, b, mb):
-            outs.append(_fdn(cx, x[s:s + mb].contiguous(), ratio[s:s + mb].contiguous(), self._variant))
+        with _on_device(x):       # kernels launch on the input's device, whatever the caller's current device is
+            for s in range(0, b, mb):
+                outs.append(_fdn(cx, x[s:s + mb].contiguous(), ratio[s:s + mb].contiguous(), self._variant))
         res = [torch.cat([o[i] for o in outs], 0) if len(outs) > 1 else outs[0][i] for i in range(4)]
         if self._variant == "lolv1":
             return res[0], res[0], res[0], res[0]
@@ -625,10 +660,17 @@ class FDformer(_Net):
     def forward(self, inp_img, ori_img=None, x_high1=None, x_high2=None, x_high3=None, x_high12=None, x_high22=None,
                 x_high32=None, x1=None, x2=None, x3=None):
         x = _check_input(inp_img, 32)
-        f = lambda t: t.detach().float().contiguous()
+        b, _, h, w = x.shape
+        sides = []
+        for lvl, (amp, pha, img) in enumerate(((x_high1, x_high12, x1), (x_high2, x_high22, x2), (x_high3, x_high32, x3))):
+            hl, wl = h >> lvl, w >> lvl
+            sides.append((_side(amp, "x_high%d" % (lvl + 1), (b, 3, hl, wl // 2 + 1), x.device),
+                          _side(pha, "x_high%d2" % (lvl + 1), (b, 3, hl, wl // 2 + 1), x.device),
+                          _side(img, "x%d" % (lvl + 1), (b, 3, hl, wl), x.device)))
+        ori = None if ori_img is None else _side(ori_img, "ori_img", x.shape, x.device)
         cx = self._context()
-        return _fdformer(cx, x, (f(x_high1), f(x_high12), f(x1)), (f(x_high2), f(x_high22), f(x2)),
-                         (f(x_high3), f(x_high32), f(x3)), "", None if ori_img is None else f(ori_img))
+        with _on_device(x):
+            return _fdformer(cx, x, sides[0], sides[1], sides[2], "", ori)
 
 
 class MAR(_Net):
@@ -654,8 +696,9 @@ class MAR(_Net):
         if use_ratio:
             if ratio is None:
                 raise RuntimeError("ratio is required")
-            r = ratio.detach().float().reshape(-1).contiguous().to(x.device)
-        return _mar(self._context(), x, r, "", self.variant, use_ratio)
+            r = _flat_ratio(ratio, x.shape[0], x.device)
+        with _on_device(x):
+            return _mar(self._context(), x, r, "", self.variant, use_ratio)
 
 
 class I_predict_net(_Net):
@@ -669,6 +712,10 @@ class I_predict_net(_Net):
     def forward(self, x, use_ori_i=False):
         ops._device_ok(x)
         x = x.detach().float().contiguous()
+        with _on_device(x):
+            return self._forward(x, use_ori_i)
+
+    def _forward(self, x, use_ori_i):
         cx = self._context()
         b, _, h, w = x.shape
         gray = None

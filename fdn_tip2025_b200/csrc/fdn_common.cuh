@@ -37,6 +37,15 @@ int fdn_check_launch(const char* what);   // returns 0 or the cudaError_t of the
         }                                                                        \
     } while (0)
 
+// Library state that depends on the GPU (twiddle tables, cudaFuncSetAttribute opt-ins, SM counts) is kept per device: one
+// process may drive several GPUs from worker threads, each with its own current device (SURVEY.md section 8(b) "Threading / streams").
+#define FDN_MAX_DEVICES 64
+static inline int fdn_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < FDN_MAX_DEVICES) ? d : 0;
+}
+
 static inline bool fdn_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline int fdn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

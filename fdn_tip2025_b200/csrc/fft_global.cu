@@ -32,15 +32,26 @@ struct FftPlanDev {
 // ---------------------------------------------------------------------------------------------------
 // host: plan cache
 // ---------------------------------------------------------------------------------------------------
+// Twiddle tables live in the memory of the device that was current when they were created, so the cache key is (device, N).
 static std::mutex g_plan_mutex;
-static std::map<int, FftPlanDev> g_plans;
+static std::map<std::pair<int, int>, FftPlanDev> g_plans;
 
-static int fdn_fft_get_plan(int N, FftPlanDev* out) {
+// st: the stream the first kernel using the table will run on.  A missing table cannot be created while that stream is being
+// captured into a CUDA graph (cudaMalloc / a synchronous upload are illegal there): call fdn_fft_prepare(H, W) before capturing.
+static int fdn_fft_get_plan(int N, FftPlanDev* out, cudaStream_t st = nullptr) {
     std::lock_guard<std::mutex> lock(g_plan_mutex);
-    auto it = g_plans.find(N);
+    const std::pair<int, int> key(fdn_device(), N);
+    auto it = g_plans.find(key);
     if (it != g_plans.end()) {
         *out = it->second;
         return 0;
+    }
+    if (st != nullptr) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+            fdn_set_error("FFT twiddle table for this length is missing while the stream is capturing: call fdn_fft_prepare(H, W) first");
+            return -3;
+        }
     }
     FftPlanDev p;
     p.N = N;
@@ -76,8 +87,11 @@ static int fdn_fft_get_plan(int N, FftPlanDev* out) {
     float2* dev = nullptr;
     if (cudaMalloc((void**)&dev, sizeof(float2) * N) != cudaSuccess) return -2;
     if (cudaMemcpy(dev, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+    // the copy from pageable memory may return before the DMA has landed, and the caller's (non-blocking) stream is not ordered
+    // against the legacy default stream: wait for the device once, at table creation
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
     p.tw = dev;
-    g_plans[N] = p;
+    g_plans[key] = p;
     *out = p;
     return 0;
 }
@@ -606,7 +620,7 @@ FDN_API int fdn_fft_rows_r2c(const float* x, float* spec, int planes, int H, int
     FDN_REQUIRE(W % 2 == 0, "the real-packed row transform needs an even width");
     FDN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0, "x must be 8-byte aligned");
     FftPlanDev PM, PW;
-    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM) == 0 && fdn_fft_get_plan(W, &PW) == 0, "plan creation failed");
+    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM, st) == 0 && fdn_fft_get_plan(W, &PW, st) == 0, "plan creation failed");
     int nrows = planes * H;
     if (fft_fast_enabled()) {
         int frc = fft_fast_rows_r2c(x, reinterpret_cast<float2*>(spec), W / 2, PM.tw, PW.tw, nrows, st);
@@ -627,7 +641,7 @@ FDN_API int fdn_fft_rows_c2r(const float* spec, float* y, int planes, int H, int
     FDN_REQUIRE(W % 2 == 0, "the real-packed row transform needs an even width");
     FDN_REQUIRE((reinterpret_cast<uintptr_t>(y) & 7) == 0 && (!res || (reinterpret_cast<uintptr_t>(res) & 7) == 0), "y/res must be 8-byte aligned");
     FftPlanDev PM, PW;
-    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM) == 0 && fdn_fft_get_plan(W, &PW) == 0, "plan creation failed");
+    FDN_REQUIRE(fdn_fft_get_plan(W / 2, &PM, st) == 0 && fdn_fft_get_plan(W, &PW, st) == 0, "plan creation failed");
     RowsC2RParams q;
     q.in = reinterpret_cast<const float2*>(spec);
     q.out = y;
@@ -659,7 +673,7 @@ FDN_API int fdn_fft_cols(const float* in, long long in_ps, int in_rs, float* out
     FDN_REQUIRE(mode >= 0 && mode <= 4, "bad mode");
     if (mode == COLS_FWD_MOD_INV) FDN_REQUIRE(C > 0 && amp && pha && w_xa && w_xp && planes % C == 0, "modulation needs maps and weights");
     FftPlanDev P;
-    FDN_REQUIRE(fdn_fft_get_plan(H, &P) == 0, "plan creation failed");
+    FDN_REQUIRE(fdn_fft_get_plan(H, &P, st) == 0, "plan creation failed");
     ColsParams q;
     q.in = reinterpret_cast<const float2*>(in);
     q.out = reinterpret_cast<float2*>(out);

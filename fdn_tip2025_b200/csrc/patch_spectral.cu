@@ -473,11 +473,12 @@ FDN_API int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, 
     FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
     FDN_REQUIRE(fdn_aligned16(out), "out must be 16-byte aligned");
     const size_t smem = (size_t)FS_C * (FS_HP * FS_HP + FS_SP * FS_SP + FS_T * FS_T) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[FDN_MAX_DEVICES] = {};
+    const int dev = fdn_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_fdffn_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid(fdn_cdiv(W, FS_T) * fdn_cdiv(H, FS_T), fdn_cdiv(C, FS_C), B);
     FDN_LAUNCH(k_fdffn_spatial, grid, dim3(256), smem, st, h, wa, wb, reinterpret_cast<const float2*>(wspec), out, C, H, W);

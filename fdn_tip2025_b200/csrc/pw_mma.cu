@@ -888,13 +888,14 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     while (q.tmem_cols < q.nbuf * set_cols) q.tmem_cols <<= 1;
     FDN_REQUIRE(q.tmem_cols <= 512, "accumulators do not fit in tensor memory");
     FDN_REQUIRE(nkb * MMA_KB <= 1024 && q.Kreal <= MMA_MAX_K, "too many input channels");
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
+    const int dev = fdn_device();
+    static int num_sms_dev[FDN_MAX_DEVICES] = {0};
+    if (num_sms_dev[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        num_sms_dev[dev] = n > 0 ? n : 148;
     }
+    const int num_sms = num_sms_dev[dev];
     const int ntiles = fdn_cdiv(HW, MMA_TP) * B;
     const int gx = min(ntiles, max(1, num_sms / nchunks));
     void (*kern)(PwMmaParams) = nullptr;
@@ -908,12 +909,12 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
         case 6: kern = k_pw_mma<3, 1>; break;
         default: kern = k_pw_mma<3, 3>; break;
     }
-    static bool configured[8] = {false, false, false, false, false, false, false, false};
+    static bool configured[FDN_MAX_DEVICES][8] = {};      // the opt-in is a per-device function attribute
     const int ki = prologue * 2 + (passes == 3 ? 1 : 0);
-    if (!configured[ki]) {
+    if (!configured[dev][ki]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
-        configured[ki] = true;
+        configured[dev][ki] = true;
     }
     kern<<<dim3(gx, nchunks, 1), dim3(MMA_THREADS), plan.smem, st>>>(q);
     return fdn_check_launch("k_pw_mma");

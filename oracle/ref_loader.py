@@ -1,7 +1,8 @@
 """Import the reference arch files by path (build container only; TEST INFRASTRUCTURE).
 
-``/root/reference`` does not exist on the GPU box, so only ``oracle/validate_against_reference.py`` and
-``tests/golden/make_golden.py`` use this.  The arch files are loaded one by one with importlib because
+``/root/reference`` does not exist on the GPU box; there the files staged by ``oracle/stage_ref.py`` under
+``oracle/_ref/`` are used (bench.py's reference arm / cpu_baseline leg).  Otherwise only
+``oracle/validate_against_reference.py`` and ``tests/golden/make_golden.py`` use this.  The arch files are loaded one by one with importlib because
 ``import basicsr`` needs lmdb/skimage which are not installed; the hard-coded
 ``torch.load('/data/tuluwei/...')`` inside ``FDN.__init__`` (FDN_arch.py:860-862) is stubbed while
 constructing.
@@ -16,6 +17,9 @@ import torch
 
 REF_ROOT = os.environ.get("FDN_REFERENCE_ROOT", "/root/reference")
 ARCH_DIR = os.path.join(REF_ROOT, "basicsr", "models", "archs")
+if not os.path.isfile(os.path.join(ARCH_DIR, "FDN_arch.py")):
+    # GPU box: the unmodified arch files staged by oracle/stage_ref.py (git-ignored, shipped with the snapshot)
+    ARCH_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "basicsr", "models", "archs")
 
 
 def available():

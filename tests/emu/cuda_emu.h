@@ -50,6 +50,10 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int,
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1 };
+static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) { *s = cudaStreamCaptureStatusNone; return 0; }
 
 #define __global__
 #define __device__

@@ -207,13 +207,12 @@ def _ctx_for(table, sd, dev):
     return net._context()
 
 
-def case_tblock(dev, dim, h, w, att, light, seed=0, report=None):
+def case_tblock(dev, dim, h, w, att, light, seed=0, report=None, b=2):
     from collections import OrderedDict
     table = OrderedDict()
     schema.transformer_block(table, "blk.", dim, att, light)
     sd = synth.make_state_dict(table, seed=seed)
     cx = _ctx_for(table, sd, dev)
-    b = 2
     x = rnd(b, dim, h, w, seed=seed + 1)
     wf = w // 2 + 1
     amp = rnd(b, 3, h, wf, seed=seed + 2).abs() * 3
@@ -288,7 +287,7 @@ def case_lpnet(dev, h, w, report=None, sd=None):
         compare("LPNet %dx%d ori=%s" % (h, w, ori), got, ref, rel_l2=1e-5, max_rel=1e-5, report=report)
 
 
-def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03):
+def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03, images=None):
     """End-to-end gate with damped weights against the fp64 oracle.
 
     strict: the north-star gate, max-abs <= 1e-3 and PSNR >= 50 dB.
@@ -304,7 +303,7 @@ def case_fdn(dev, kind, h, w, b=1, report=None, seed=7, strict=True, damp=0.03):
     net = getattr(archs, kind)()
     net.load_state_dict(sd, strict=True)
     net = net.to(dev)
-    x = synth.low_light_images(b, h, w)
+    x = synth.low_light_images(b, h, w) if images is None else images
     ratio = torch.full((b, 1), 0.35)
     got = net(x.to(dev), ratio_i=ratio.to(dev))
     sync(dev)

@@ -8,9 +8,16 @@ import parity_cases as P
 
 @pytest.fixture(scope="module")
 def emu():
+    import os
     from emu import harness
     harness.enable()
+    old = os.environ.get("FDN_B200_GEMM")
+    os.environ["FDN_B200_GEMM"] = "ffma"      # the emulation build has no tcgen05 kernel and the package never downgrades silently
     yield "cpu"
+    if old is None:
+        os.environ.pop("FDN_B200_GEMM", None)
+    else:
+        os.environ["FDN_B200_GEMM"] = old
     # restore the product loader so later tests see the real library
     from fdn_tip2025_b200 import _lib, ops
     import importlib
