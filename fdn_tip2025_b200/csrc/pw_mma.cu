@@ -45,6 +45,7 @@
 #define MMA_LOAD_WARP0 17     // three loader warps: a warp retires its lanes' bulk copies one after another (~60 cycles each), so the copy issue rate scales with the number of loader warps; 20 warps still get 96 registers each (a 21st caps them at 80 and spills)
 #define MMA_LOAD_THREADS 96
 #define MMA_THREADS 640
+#define MMA_THREADS_LD1 576   // LD = 1: producers 0-7, epilogue 8-15, MMA 16, weight-panel loader 17
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
@@ -153,6 +154,20 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's committed cp.async groups are pending (n is CTA-uniform, 0..7)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -232,8 +247,13 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
         if (FULL || j < nvalid) op[j * HW] = acc[j];
 }
 
-template <int PRO, int PASSES>
-__global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
+// LD = 0: the loader warps stream the raw ring with one TMA bulk copy per 512-byte channel row (round 1).
+// LD = 1: the 256 producer threads fetch the raw ring themselves with 16-byte cp.async (a warp moves one 512-byte row per
+//         instruction, four rows per K block) tracked with commit / wait groups and one named barrier per K block; no loader
+//         warps (576 threads), no raw_full / raw_empty barriers.  The per-row bulk copies cap the ring at ~58 cycles per row
+//         and SM (2.6 TB/s) whoever issues them (tools/ubench); cp.async is not bound by the TMA unit's request rate.
+template <int PRO, int PASSES, int LD>
+__global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align by pointer arithmetic on the shared array (an integer round trip would turn every access into a generic LD/ST)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -268,7 +288,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const int gsize = PRO == 2 ? q.E : q.K;
 
     if (tid == 0) {
-        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS / 32); }
+        if (LD == 0)
+            for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS / 32); }
         for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS / 32 + (q.b_resident ? 0 : 1)); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     const uint32_t tmem_base = *s_tmem;
     const int nmain = q.nmain;
     unsigned long long w0 = 0, w1 = 0;            // debug: cycles spent waiting (recorded by one thread per role)
-    const bool rec = FDN_MMA_PROFILE && q.dbg != nullptr && (tid == 0 || tid == MMA_EPI_WARP0 * 32 || tid == MMA_MMA_WARP * 32 || tid == MMA_LOAD_WARP0 * 32);
+    const bool rec = FDN_MMA_PROFILE && q.dbg != nullptr && (tid == 0 || tid == MMA_EPI_WARP0 * 32 || tid == MMA_MMA_WARP * 32 || (LD == 0 && tid == MMA_LOAD_WARP0 * 32));
     const long long t_start = FDN_MMA_PROFILE ? clock64() : 0;
 
     if (warp >= MMA_LOAD_WARP0) {
@@ -319,7 +340,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         // raw_full[r] is deferred by the hardware until its copies have landed
         const int lt = tid - MMA_LOAD_WARP0 * 32;
         uint32_t lit = 0;
-        if (!q.b_resident && warp == MMA_LOAD_WARP0 + MMA_LOAD_THREADS / 32 - 1) {
+        if (!q.b_resident && warp == (LD ? MMA_LOAD_WARP0 : MMA_LOAD_WARP0 + MMA_LOAD_THREADS / 32 - 1)) {
             // weight panels that do not fit in shared memory: one contiguous TMA bulk copy per K block straight into the
             // operand stage (the packed image is contiguous in global memory); completion counts on a_full[s]
             if (lane == 0) {
@@ -333,6 +354,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                         bulk_g2s(s_stage + s * stage_bytes + 2 * a_bytes, bsrc + (size_t)kb * 2 * q.Nc * 32, bytes, &a_full[s]);
                     }
             }
+        } else if (LD == 1) {
+            // nothing to do: the producers fetch their own ring
         } else if (q.bulk) {
             // one TMA bulk copy (512 contiguous bytes) per channel row.  Issuing a bulk copy costs ~60 cycles of one thread's
             // uniform datapath, so the rows of every K block are interleaved over all loader warps that do not stream weights.
@@ -433,6 +456,51 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
         uint32_t soff[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) soff[i] = sw128_off(pix, half + 2 * i);
+        // ---- LD = 1: this thread's share of the raw-ring fetches.  K block number j of the CTA's (tile, kb) sequence goes to ring slot
+        // j % ring; warp w copies rows w, w + 8, ... of the block, lane l the 16-byte piece l of the row.  Every call commits exactly
+        // one (possibly empty) group, so "at most n groups pending" identifies K blocks.
+        int ld_tile = blockIdx.x, ld_kb = 0;
+        uint32_t ld_j = 0;
+        auto issue_next = [&]() {
+            if (ld_tile < ntiles) {
+                const int b = ld_tile / tiles_per_img, p0 = (ld_tile - b * tiles_per_img) * MMA_TP;
+                unsigned char* slot = s_raw + (size_t)(ld_j % (uint32_t)q.ring) * slot_bytes + lane * 16;
+                if (p0 + lane * 4 < HW) {
+                    const size_t px = (size_t)p0 + lane * 4;
+                    if (PRO == 2) {
+                        // grouped layout (see the loader above): virtual rows 0..29 gate inputs, 30..39 v_value, 40..45 statistics
+                        const int ne = min(MMA_EB, q.E - ld_kb * MMA_EB);
+                        for (int vi = warp; vi < 4 * MMA_EB + 6; vi += MMA_PROD_THREADS / 32) {
+                            const int g = vi / MMA_EB, el = vi - g * MMA_EB;
+                            if (g < 3) {
+                                if (el < ne) cp_async16(slot + vi * (MMA_TP * 4), q.src0 + ((size_t)b * q.C0 + g * q.E + ld_kb * MMA_EB + el) * HW + px);
+                            } else if (g == 3) {
+                                if (el < ne) cp_async16(slot + MMA_P2_V_OFF + el * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(ld_kb * MMA_EB + el) * HW + px);
+                            } else if (ld_kb == 0 && q.stats) {
+                                const int sr = vi - 4 * MMA_EB;
+                                cp_async16(slot + MMA_P2_ST_OFF + sr * (MMA_TP * 4), q.stats + ((size_t)b * 6 + sr) * HW + px);
+                            }
+                        }
+                    } else {
+                        const int rows = min(MMA_KB, q.K - ld_kb * MMA_KB);
+#pragma unroll
+                        for (int r4 = 0; r4 < MMA_KB / (MMA_PROD_THREADS / 32); ++r4) {
+                            const int row = warp + r4 * (MMA_PROD_THREADS / 32);
+                            if (row < rows) {
+                                const int k = ld_kb * MMA_KB + row;
+                                cp_async16(slot + row * (MMA_TP * 4), src_row(q, b, k) + px);
+                                if (has_aux) cp_async16(slot + MMA_SLOT_BYTES + row * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)k * HW + px);
+                            }
+                        }
+                    }
+                }
+                if (++ld_kb == nkb) { ld_kb = 0; ld_tile += gridDim.x; }
+            }
+            ++ld_j;
+            cp_async_commit();
+        };
+        if (LD == 1)
+            for (int j = 0; j < q.ring - 1; ++j) issue_next();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
             float mu = 0.f, rs = 1.f;
@@ -440,8 +508,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             if (PRO == 1 || PRO == 3) {
                 // LayerNorm statistics over all K channels of this pixel, from the raw ring (all K blocks of the tile)
                 float s = 0.f;
+                if (LD == 1) {          // every K block of this tile has landed (ring >= nkb + 1: K blocks it .. it + ring - 2 are in flight)
+                    cp_async_wait_dyn(q.ring - 1 - nkb);
+                    prod_sync();
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
+                    if (LD == 0) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
                     const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
                     const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
 #pragma unroll
@@ -476,7 +548,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     constexpr int HALF = decltype(half_c)::value;
                     acc[0] = acc[1] = acc[2] = 0.f;
                     for (int kb = 0; kb < nkb; ++kb) {
-                        if (!second) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
+                        if (LD == 0 && !second) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
                         const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
                         const int ne = min(MMA_EB, q.E - kb * MMA_EB);
 #pragma unroll
@@ -493,6 +565,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                     }
                 };
                 float acc[3];
+                if (LD == 1) {
+                    cp_async_wait_dyn(q.ring - 1 - nkb);
+                    prod_sync();
+                }
                 if (half == 0) group_pass(std::integral_constant<int, 0>{}, 0.f, 0.f, 0.f, false, acc);
                 else group_pass(std::integral_constant<int, 1>{}, 0.f, 0.f, 0.f, false, acc);
                 prod_sync();                       // the previous tile's readers of s_part are done
@@ -516,7 +592,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int r = it % q.ring;
                 const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
-                mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
+                if (LD == 0) {
+                    mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
+                } else {
+                    cp_async_wait_dyn(q.ring - 2);      // this thread's pieces of K block `it` have landed ...
+                    prod_sync();                        // ... and everybody's; all producers are also done with block it - 1,
+                    issue_next();                       // whose slot receives block it + ring - 1
+                }
                 if (PRO == 2 && kb == 0 && q.stats != nullptr) {
                     const float* st = raw + MMA_P2_ST_OFF / 4;
                     gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
@@ -577,7 +659,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&raw_empty[r]);        // the warp is done with the raw slot
+                    if (LD == 0) mbar_arrive(&raw_empty[r]);        // the warp is done with the raw slot
                     mbar_arrive(&a_full[s]);
                 }
             }
@@ -752,12 +834,14 @@ __global__ void __launch_bounds__(256) k_group_stats(const float* __restrict__ x
 
 struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 
-static bool pw_mma_plan(int Nc, int nkb, int prologue, bool ring_holds_tile, PwMmaPlan* out) {
+static bool pw_mma_plan(int Nc, int nkb, int prologue, bool ring_holds_tile, int ld, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
     const size_t slot = prologue == 2 ? (size_t)MMA_P2_SLOT : (size_t)MMA_SLOT_BYTES * (prologue == 3 ? 2 : 1);
     const size_t misc = 1024 + (6 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 12) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
-    const int ring_min = ring_holds_tile ? max(nkb, 2) : 2;  // LayerNorm statistics need all K blocks of a tile resident
+    // LayerNorm statistics need all K blocks of a tile resident; with the producers' own cp.async ring (ld = 1) one more slot, because
+    // the slot of the K block converted last is refilled only after the next block's barrier
+    const int ring_min = ring_holds_tile ? max(nkb + ld, 2) : 2 + ld;
     PwMmaPlan best;
     bool found = false;
     int ns_hi = 2, ns_lo = 1;                 // operand stages; FDN_MMA_NSTAGE pins the count (dev knob, up to 4)
@@ -855,7 +939,10 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
     PwMmaPlan plan;
-    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), &plan), "tile does not fit in shared memory");
+    // raw-ring loader: 1 = 16-byte cp.async issued by the producer warps (default), 0 = per-row TMA bulk copies from loader warps
+    static const int ld_env = getenv("FDN_MMA_LOADER") ? atoi(getenv("FDN_MMA_LOADER")) : 1;
+    const int ld = ld_env ? 1 : 0;
+    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), ld, &plan), "tile does not fit in shared memory");
     q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
     // accumulators: one K block (<= 12 accumulations) needs no split; longer K keeps hi*hi and the corrections apart and
     // spreads the K blocks over up to three main accumulators
@@ -899,24 +986,32 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     const int ntiles = fdn_cdiv(HW, MMA_TP) * B;
     const int gx = min(ntiles, max(1, num_sms / nchunks));
     void (*kern)(PwMmaParams) = nullptr;
-    switch (prologue * 2 + (passes == 3 ? 1 : 0)) {
-        case 0: kern = k_pw_mma<0, 1>; break;
-        case 1: kern = k_pw_mma<0, 3>; break;
-        case 2: kern = k_pw_mma<1, 1>; break;
-        case 3: kern = k_pw_mma<1, 3>; break;
-        case 4: kern = k_pw_mma<2, 1>; break;
-        case 5: kern = k_pw_mma<2, 3>; break;
-        case 6: kern = k_pw_mma<3, 1>; break;
-        default: kern = k_pw_mma<3, 3>; break;
+    switch ((prologue * 2 + (passes == 3 ? 1 : 0)) * 2 + ld) {
+        case 0: kern = k_pw_mma<0, 1, 0>; break;
+        case 1: kern = k_pw_mma<0, 1, 1>; break;
+        case 2: kern = k_pw_mma<0, 3, 0>; break;
+        case 3: kern = k_pw_mma<0, 3, 1>; break;
+        case 4: kern = k_pw_mma<1, 1, 0>; break;
+        case 5: kern = k_pw_mma<1, 1, 1>; break;
+        case 6: kern = k_pw_mma<1, 3, 0>; break;
+        case 7: kern = k_pw_mma<1, 3, 1>; break;
+        case 8: kern = k_pw_mma<2, 1, 0>; break;
+        case 9: kern = k_pw_mma<2, 1, 1>; break;
+        case 10: kern = k_pw_mma<2, 3, 0>; break;
+        case 11: kern = k_pw_mma<2, 3, 1>; break;
+        case 12: kern = k_pw_mma<3, 1, 0>; break;
+        case 13: kern = k_pw_mma<3, 1, 1>; break;
+        case 14: kern = k_pw_mma<3, 3, 0>; break;
+        default: kern = k_pw_mma<3, 3, 1>; break;
     }
-    static bool configured[FDN_MAX_DEVICES][8] = {};      // the opt-in is a per-device function attribute
-    const int ki = prologue * 2 + (passes == 3 ? 1 : 0);
+    static bool configured[FDN_MAX_DEVICES][16] = {};      // the opt-in is a per-device function attribute
+    const int ki = (prologue * 2 + (passes == 3 ? 1 : 0)) * 2 + ld;
     if (!configured[dev][ki]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
         configured[dev][ki] = true;
     }
-    kern<<<dim3(gx, nchunks, 1), dim3(MMA_THREADS), plan.smem, st>>>(q);
+    kern<<<dim3(gx, nchunks, 1), dim3(ld ? MMA_THREADS_LD1 : MMA_THREADS), plan.smem, st>>>(q);
     return fdn_check_launch("k_pw_mma");
 #endif
 }

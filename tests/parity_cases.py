@@ -47,6 +47,36 @@ def compare(name, got, ref64, rel_l2=1e-5, max_rel=2e-4, report=None):
     return l2, mx
 
 
+def compare_patchwise(name, got, ref64, rel_l2=1e-5, max_rel=2e-4, max_bad=None, report=None):
+    """Block gate for full-size planes: like compare(), but evaluated per 8x8 patch so that an isolated FDSA sign event does not
+    hide everything else.  FDSA takes the phase of every 8x8 bin; a self-conjugate (purely real) bin whose value is at rounding level
+    gets its sign - a phase of 0 or pi - from rounding noise, which flips one (patch, channel) of the output in ANY fp32 evaluation:
+    at 640x1120 (11 200 patches x 38 channels x 12 such bins) torch's own fp32 forward differs from its fp64 forward in exactly one
+    patch (rel-L2 7.45e-05, max 1.4e-02 of |y|inf - measured with oracle/fdn_oracle.py, the numbers this kernel reproduces to four
+    digits) while the other 11 199 patches agree to 1.7e-07.  Gate: at most `max_bad` patches (default max(2, 2e-4 of all)) may
+    exceed max_rel * |y|inf; all the others together must meet rel_l2 and max_rel."""
+    got = got.detach().double().cpu()
+    ref64 = ref64.detach().double().cpu()
+    assert got.shape == ref64.shape and torch.isfinite(got).all(), name
+    b, c, h, w = got.shape
+    d = got - ref64
+    ymax = ref64.abs().max().clamp_min(1e-30).item()
+    pe = d.abs().amax(1).reshape(b, h // 8, 8, w // 8, 8).amax((2, 4))            # worst error of each patch over channels
+    bad = pe > max_rel * ymax
+    nbad, npatch = int(bad.sum().item()), pe.numel()
+    limit = max(2, int(2e-4 * npatch)) if max_bad is None else max_bad
+    good = (~bad)[:, None, :, None, :, None].expand(b, c, h // 8, 8, w // 8, 8).reshape(b, c, h, w)
+    dg = d[good]
+    l2 = (dg.norm() / ref64[good].norm().clamp_min(1e-30)).item()
+    mx = dg.abs().max().item() / ymax
+    if report is not None:
+        report.append((name, l2, mx, "event patches %d of %d" % (nbad, npatch), "all-patch max %.2e" % (d.abs().max().item() / ymax)))
+    assert nbad <= limit, "%s: %d of %d patches beyond %.1e |y|inf (limit %d)" % (name, nbad, npatch, max_rel, limit)
+    assert l2 <= rel_l2 and mx <= max_rel, "%s: rel-L2 %.3e (<= %.1e), max-abs/|y|inf %.3e (<= %.1e) outside %d event patches" % (
+        name, l2, rel_l2, mx, max_rel, nbad)
+    return l2, mx, nbad
+
+
 # ----------------------------------------------------------------------------------------- single operators
 def case_rfft2_irfft2(dev, h, w, planes=3):
     x = rnd(planes, h, w, seed=h * 1000 + w)
@@ -207,7 +237,7 @@ def _ctx_for(table, sd, dev):
     return net._context()
 
 
-def case_tblock(dev, dim, h, w, att, light, seed=0, report=None, b=2):
+def case_tblock(dev, dim, h, w, att, light, seed=0, report=None, b=2, patchwise=False):
     from collections import OrderedDict
     table = OrderedDict()
     schema.transformer_block(table, "blk.", dim, att, light)
@@ -227,7 +257,7 @@ def case_tblock(dev, dim, h, w, att, light, seed=0, report=None, b=2):
         got = archs._fdsa(cx, xd, "blk.")
         sync(dev)
         ref = f64(x) + O.fdsa(O.layer_norm(f64(x), sd64, "blk.norm1."), sd64, "blk.attn.")
-        compare("FDSA dim %d" % dim, got, ref, report=report)
+        (compare_patchwise if patchwise else compare)("FDSA dim %d" % dim, got, ref, report=report)
     got = archs._fdffn(cx, xd, "blk.")
     sync(dev)
     ref = f64(x) + O.fdffn(O.layer_norm(f64(x), sd64, "blk.norm2."), sd64, "blk.ffn.")
