@@ -49,6 +49,8 @@ SIGNATURES = {
     "fdn_gray_mean": "ppiis",
     "fdn_pre_u8hwc_to_f32chw": "ppiiiiis",
     "fdn_post_f32chw_to_u8hwc": "ppiiiiis",
+    "fdn_psnr": "ppppiiiiiis",
+    "fdn_ssim": "ppppiiiiiis",
 }
 _CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P}
 

@@ -45,7 +45,6 @@
 #define MMA_LOAD_WARP0 17     // three loader warps: a warp retires its lanes' bulk copies one after another (~60 cycles each), so the copy issue rate scales with the number of loader warps; 20 warps still get 96 registers each (a 21st caps them at 80 and spills)
 #define MMA_LOAD_THREADS 96
 #define MMA_THREADS 640
-#define MMA_THREADS_LD1 576   // LD = 1: producers 0-7, epilogue 8-15, MMA 16, weight-panel loader 17
 #define MMA_MAX_K 512        // LayerNorm gamma/beta staged in shared memory
 #define MMA_MAX_RING 8
 #define MMA_SLOT_BYTES (MMA_KB * MMA_TP * 4)   // 16 KB: one raw K block
@@ -154,20 +153,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most n of this thread's committed cp.async groups are pending (n is CTA-uniform, 0..7)
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-    }
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -193,6 +178,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
+// Position in a ring of n slots plus the parity of the current round: the roles walk their rings with an increment, a compare and
+// an xor instead of it % n and it / n on run-time n (each ~20 instructions through MUFU.RCP; the single-warp MMA loop spent most of
+// its ~270 instructions per K block on them and capped the kernel at ~2000 cycles per K block in round 1).
+struct RingPos {
+    int idx;
+    uint32_t par;
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) { idx = 0; par ^= 1u; }
+    }
+};
 __device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // issue only; call tmem_ld_wait() before using the registers
@@ -214,7 +209,7 @@ __device__ __forceinline__ const float* src_row(const PwMmaParams& q, int b, int
 // store (out may alias res for in-place residuals); null pointers switch a stage off in the generic instantiation, offsets stay 32-bit (16 planes * HW * 4 B < 2^31 for any image we accept).
 template <bool FULL, bool RES, bool FILM, bool BIAS>
 __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const float* rp, const float* fm, const float* fa,
-                                          const float* bias, const float (&rpre)[16], bool pre, float res_coef, int HW, int nvalid) {
+                                          const float* bias, const float (&rpre)[16], bool pre, float res_coef, uint32_t HW, int nvalid) {
     if (BIAS && bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -223,7 +218,7 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
     if (FILM && fm != nullptr) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (FULL || j < nvalid) acc[j] = acc[j] * fm[j * HW] + fa[j * HW];
+            if (FULL || j < nvalid) acc[j] = acc[j] * fm[(size_t)HW * j] + fa[(size_t)HW * j];
     }
     if (RES) {
         if (pre) {
@@ -235,7 +230,7 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
                 float r[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (FULL || h + j < nvalid) r[j] = rp[(h + j) * HW];
+                    if (FULL || h + j < nvalid) r[j] = rp[(size_t)HW * (h + j)];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (FULL || h + j < nvalid) acc[h + j] += res_coef * r[j];
@@ -244,16 +239,11 @@ __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const flo
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-        if (FULL || j < nvalid) op[j * HW] = acc[j];
+        if (FULL || j < nvalid) op[(size_t)HW * j] = acc[j];
 }
 
-// LD = 0: the loader warps stream the raw ring with one TMA bulk copy per 512-byte channel row (round 1).
-// LD = 1: the 256 producer threads fetch the raw ring themselves with 16-byte cp.async (a warp moves one 512-byte row per
-//         instruction, four rows per K block) tracked with commit / wait groups and one named barrier per K block; no loader
-//         warps (576 threads), no raw_full / raw_empty barriers.  The per-row bulk copies cap the ring at ~58 cycles per row
-//         and SM (2.6 TB/s) whoever issues them (tools/ubench); cp.async is not bound by the TMA unit's request rate.
-template <int PRO, int PASSES, int LD>
-__global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
+template <int PRO, int PASSES>
+__global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align by pointer arithmetic on the shared array (an integer round trip would turn every access into a generic LD/ST)
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -288,8 +278,7 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
     const int gsize = PRO == 2 ? q.E : q.K;
 
     if (tid == 0) {
-        if (LD == 0)
-            for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS / 32); }
+        for (int i = 0; i < q.ring; ++i) { mbar_init(&raw_full[i], q.bulk ? 1 : (q.b_resident ? MMA_LOAD_THREADS : MMA_LOAD_THREADS - 32)); mbar_init(&raw_empty[i], MMA_PROD_THREADS / 32); }
         for (int i = 0; i < q.nstage; ++i) { mbar_init(&a_full[i], MMA_PROD_THREADS / 32 + (q.b_resident ? 0 : 1)); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], MMA_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -331,7 +320,7 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
     const uint32_t tmem_base = *s_tmem;
     const int nmain = q.nmain;
     unsigned long long w0 = 0, w1 = 0;            // debug: cycles spent waiting (recorded by one thread per role)
-    const bool rec = FDN_MMA_PROFILE && q.dbg != nullptr && (tid == 0 || tid == MMA_EPI_WARP0 * 32 || tid == MMA_MMA_WARP * 32 || (LD == 0 && tid == MMA_LOAD_WARP0 * 32));
+    const bool rec = FDN_MMA_PROFILE && q.dbg != nullptr && (tid == 0 || tid == MMA_EPI_WARP0 * 32 || tid == MMA_MMA_WARP * 32 || tid == MMA_LOAD_WARP0 * 32);
     const long long t_start = FDN_MMA_PROFILE ? clock64() : 0;
 
     if (warp >= MMA_LOAD_WARP0) {
@@ -340,22 +329,21 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
         // raw_full[r] is deferred by the hardware until its copies have landed
         const int lt = tid - MMA_LOAD_WARP0 * 32;
         uint32_t lit = 0;
-        if (!q.b_resident && warp == (LD ? MMA_LOAD_WARP0 : MMA_LOAD_WARP0 + MMA_LOAD_THREADS / 32 - 1)) {
+        if (!q.b_resident && warp == MMA_LOAD_WARP0 + MMA_LOAD_THREADS / 32 - 1) {
             // weight panels that do not fit in shared memory: one contiguous TMA bulk copy per K block straight into the
             // operand stage (the packed image is contiguous in global memory); completion counts on a_full[s]
             if (lane == 0) {
-                uint32_t bit = 0;
+                RingPos sp{0, 0};
                 const uint32_t bytes = (uint32_t)panels * b_bytes;
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                    for (int kb = 0; kb < nkb; ++kb, ++bit) {
-                        const int s = bit % q.nstage;
-                        if (bit >= (uint32_t)q.nstage) mbar_wait(&a_empty[s], ((bit / q.nstage) - 1) & 1);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const int s = sp.idx;
+                        mbar_wait(&a_empty[s], sp.par ^ 1u);        // first round: the preceding phase of a fresh barrier counts as complete
                         mbar_expect_tx(&a_full[s], bytes);
                         bulk_g2s(s_stage + s * stage_bytes + 2 * a_bytes, bsrc + (size_t)kb * 2 * q.Nc * 32, bytes, &a_full[s]);
+                        sp.advance(q.nstage);
                     }
             }
-        } else if (LD == 1) {
-            // nothing to do: the producers fetch their own ring
         } else if (q.bulk) {
             // one TMA bulk copy (512 contiguous bytes) per channel row.  Issuing a bulk copy costs ~60 cycles of one thread's
             // uniform datapath, so the rows of every K block are interleaved over all loader warps that do not stream weights.
@@ -363,13 +351,14 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
             // K block use all three; with streamed weights the last loader warp carries the weight panels
             const int nlw = PRO == 2 ? (q.b_resident ? MMA_LOAD_THREADS / 32 : MMA_LOAD_THREADS / 32 - 1) : 2;
             const int lw = warp - MMA_LOAD_WARP0;
+            RingPos rp{0, 0};
             if (lw < nlw)
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                     const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
                     const uint32_t len = (uint32_t)min(MMA_TP, HW - p0) * 4;
-                    for (int kb = 0; kb < nkb; ++kb, ++lit) {
-                        const int r = lit % q.ring;
-                        if (lit >= (uint32_t)q.ring) mbar_wait_t(&raw_empty[r], ((lit / q.ring) - 1) & 1, &w0, rec);
+                    for (int kb = 0; kb < nkb; ++kb, rp.advance(q.ring)) {
+                        const int r = rp.idx;
+                        mbar_wait_t(&raw_empty[r], rp.par ^ 1u, &w0, rec);
                         unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                         if (PRO == 2) {
                             // grouped layout: row kk = g*10 + el holds channel g*E + kb*10 + el; the 10 v_value rows are loaded once;
@@ -410,7 +399,7 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
             const int vch = min(MMA_TP, HW - p0) >> 2;                        // valid 16-byte pieces per channel row
             for (int kb = 0; kb < nkb; ++kb, ++lit) {
                 const int r = lit % q.ring;
-                if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);
+                if (lit >= (uint32_t)q.ring) mbar_wait(&raw_empty[r], ((lit / q.ring) - 1) & 1);      // (FDN_MMA_BULK=0 dev path: not tuned)
                 unsigned char* slot = s_raw + (size_t)r * slot_bytes;
                 if (PRO == 2) {
                     const int ne = min(MMA_EB, q.E - kb * MMA_EB);
@@ -451,56 +440,18 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
     } else if (warp < MMA_EPI_WARP0) {
         // =============================================== producers =================================================
         const int pix = tid & (MMA_TP - 1), half = tid >> 7;
-        uint32_t it = 0;       // K-block counter (same sequence as the loader and the MMA warp)
+        RingPos rr{0, 0}, sr{0, 0};       // raw ring slot / operand stage of the next K block (same sequence as the loader and the MMA warp)
+        // raw slot of K block kb of the current tile (the statistics passes look ahead; ring >= nkb whenever they run)
+        auto ahead = [&](int kb, uint32_t& par) {
+            int i = rr.idx + kb;
+            par = rr.par;
+            if (i >= q.ring) { i -= q.ring; par ^= 1u; }
+            return i;
+        };
         // byte offsets of this thread's four 16-byte groups inside the swizzled operand panel
         uint32_t soff[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) soff[i] = sw128_off(pix, half + 2 * i);
-        // ---- LD = 1: this thread's share of the raw-ring fetches.  K block number j of the CTA's (tile, kb) sequence goes to ring slot
-        // j % ring; warp w copies rows w, w + 8, ... of the block, lane l the 16-byte piece l of the row.  Every call commits exactly
-        // one (possibly empty) group, so "at most n groups pending" identifies K blocks.
-        int ld_tile = blockIdx.x, ld_kb = 0;
-        uint32_t ld_j = 0;
-        auto issue_next = [&]() {
-            if (ld_tile < ntiles) {
-                const int b = ld_tile / tiles_per_img, p0 = (ld_tile - b * tiles_per_img) * MMA_TP;
-                unsigned char* slot = s_raw + (size_t)(ld_j % (uint32_t)q.ring) * slot_bytes + lane * 16;
-                if (p0 + lane * 4 < HW) {
-                    const size_t px = (size_t)p0 + lane * 4;
-                    if (PRO == 2) {
-                        // grouped layout (see the loader above): virtual rows 0..29 gate inputs, 30..39 v_value, 40..45 statistics
-                        const int ne = min(MMA_EB, q.E - ld_kb * MMA_EB);
-                        for (int vi = warp; vi < 4 * MMA_EB + 6; vi += MMA_PROD_THREADS / 32) {
-                            const int g = vi / MMA_EB, el = vi - g * MMA_EB;
-                            if (g < 3) {
-                                if (el < ne) cp_async16(slot + vi * (MMA_TP * 4), q.src0 + ((size_t)b * q.C0 + g * q.E + ld_kb * MMA_EB + el) * HW + px);
-                            } else if (g == 3) {
-                                if (el < ne) cp_async16(slot + MMA_P2_V_OFF + el * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)(ld_kb * MMA_EB + el) * HW + px);
-                            } else if (ld_kb == 0 && q.stats) {
-                                const int sr = vi - 4 * MMA_EB;
-                                cp_async16(slot + MMA_P2_ST_OFF + sr * (MMA_TP * 4), q.stats + ((size_t)b * 6 + sr) * HW + px);
-                            }
-                        }
-                    } else {
-                        const int rows = min(MMA_KB, q.K - ld_kb * MMA_KB);
-#pragma unroll
-                        for (int r4 = 0; r4 < MMA_KB / (MMA_PROD_THREADS / 32); ++r4) {
-                            const int row = warp + r4 * (MMA_PROD_THREADS / 32);
-                            if (row < rows) {
-                                const int k = ld_kb * MMA_KB + row;
-                                cp_async16(slot + row * (MMA_TP * 4), src_row(q, b, k) + px);
-                                if (has_aux) cp_async16(slot + MMA_SLOT_BYTES + row * (MMA_TP * 4), q.aux + (size_t)b * q.aux_bs + (size_t)k * HW + px);
-                            }
-                        }
-                    }
-                }
-                if (++ld_kb == nkb) { ld_kb = 0; ld_tile += gridDim.x; }
-            }
-            ++ld_j;
-            cp_async_commit();
-        };
-        if (LD == 1)
-            for (int j = 0; j < q.ring - 1; ++j) issue_next();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * MMA_TP;
             float mu = 0.f, rs = 1.f;
@@ -508,13 +459,11 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
             if (PRO == 1 || PRO == 3) {
                 // LayerNorm statistics over all K channels of this pixel, from the raw ring (all K blocks of the tile)
                 float s = 0.f;
-                if (LD == 1) {          // every K block of this tile has landed (ring >= nkb + 1: K blocks it .. it + ring - 2 are in flight)
-                    cp_async_wait_dyn(q.ring - 1 - nkb);
-                    prod_sync();
-                }
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (LD == 0) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
-                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                    uint32_t par;
+                    const int ri = ahead(kb, par);
+                    mbar_wait_t(&raw_full[ri], par, &w0, rec);
+                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)ri * slot_bytes) + pix;
                     const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
 #pragma unroll
                     for (int kk = 0; kk < 16; ++kk) {
@@ -528,7 +477,8 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                 mu = (s_part[pix] + s_part[MMA_TP + pix]) / (float)q.K;
                 float v = 0.f;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                    uint32_t par;
+                    const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)ahead(kb, par) * slot_bytes) + pix;
                     const int kmax = min(MMA_KB, q.K - kb * MMA_KB);
 #pragma unroll
                     for (int kk = 0; kk < 16; ++kk) {
@@ -548,8 +498,10 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                     constexpr int HALF = decltype(half_c)::value;
                     acc[0] = acc[1] = acc[2] = 0.f;
                     for (int kb = 0; kb < nkb; ++kb) {
-                        if (LD == 0 && !second) mbar_wait_t(&raw_full[(it + kb) % q.ring], ((it + kb) / q.ring) & 1, &w0, rec);
-                        const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)((it + kb) % q.ring) * slot_bytes) + pix;
+                        uint32_t par;
+                        const int ri = ahead(kb, par);
+                        if (!second) mbar_wait_t(&raw_full[ri], par, &w0, rec);
+                        const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)ri * slot_bytes) + pix;
                         const int ne = min(MMA_EB, q.E - kb * MMA_EB);
 #pragma unroll
                         for (int kk2 = 0; kk2 < 15; ++kk2) {
@@ -565,10 +517,6 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                     }
                 };
                 float acc[3];
-                if (LD == 1) {
-                    cp_async_wait_dyn(q.ring - 1 - nkb);
-                    prod_sync();
-                }
                 if (half == 0) group_pass(std::integral_constant<int, 0>{}, 0.f, 0.f, 0.f, false, acc);
                 else group_pass(std::integral_constant<int, 1>{}, 0.f, 0.f, 0.f, false, acc);
                 prod_sync();                       // the previous tile's readers of s_part are done
@@ -589,25 +537,19 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                 grs1 = 1.0f / sqrtf((s_part[1 * MMA_TP + pix] + s_part[4 * MMA_TP + pix]) * invE + 1e-5f);
                 grs2 = 1.0f / sqrtf((s_part[2 * MMA_TP + pix] + s_part[5 * MMA_TP + pix]) * invE + 1e-5f);
             }
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int r = it % q.ring;
+            for (int kb = 0; kb < nkb; ++kb, rr.advance(q.ring), sr.advance(q.nstage)) {
+                const int r = rr.idx;
                 const float* raw = reinterpret_cast<const float*>(s_raw + (size_t)r * slot_bytes) + pix;
-                if (LD == 0) {
-                    mbar_wait_t(&raw_full[r], (it / q.ring) & 1, &w0, rec);
-                } else {
-                    cp_async_wait_dyn(q.ring - 2);      // this thread's pieces of K block `it` have landed ...
-                    prod_sync();                        // ... and everybody's; all producers are also done with block it - 1,
-                    issue_next();                       // whose slot receives block it + ring - 1
-                }
+                mbar_wait_t(&raw_full[r], rr.par, &w0, rec);
                 if (PRO == 2 && kb == 0 && q.stats != nullptr) {
                     const float* st = raw + MMA_P2_ST_OFF / 4;
                     gmu0 = st[0 * MMA_TP]; grs0 = st[1 * MMA_TP]; gmu1 = st[2 * MMA_TP]; grs1 = st[3 * MMA_TP];
                     gmu2 = st[4 * MMA_TP]; grs2 = st[5 * MMA_TP];
                 }
-                const int s = it % q.nstage;
+                const int s = sr.idx;
                 unsigned char* stage = s_stage + s * stage_bytes;
                 const int nchunks_used = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 2;
-                if (it >= (uint32_t)q.nstage) mbar_wait_t(&a_empty[s], ((it / q.nstage) - 1) & 1, &w1, rec);
+                mbar_wait_t(&a_empty[s], sr.par ^ 1u, &w1, rec);      // first round: passes at once
                 // The conversion is specialised on this thread's half (0/1) so that every per-element index (channel, LayerNorm
                 // group, v_value row, smem offsets) is a compile-time constant: ~3x fewer instructions than runtime indexing.
                 auto convert = [&](auto half_c) {
@@ -659,63 +601,76 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    if (LD == 0) mbar_arrive(&raw_empty[r]);        // the warp is done with the raw slot
+                    mbar_arrive(&raw_empty[r]);        // the warp is done with the raw slot
                     mbar_arrive(&a_full[s]);
                 }
             }
         }
     } else if (warp == MMA_MMA_WARP) {
         // =============================================== MMA issuer ================================================
-        uint32_t it = 0, titer = 0;
-        const uint32_t set_cols = (uint32_t)q.set_cols;
+        // One lane issues everything, so this loop is serial, latency-bound scalar code: shared-memory descriptors are advanced with
+        // integer adds from a constant template (the 14-bit address field cannot carry: shared memory ends below 256 KB) and the
+        // stage / accumulator indices are counters.
+        uint32_t titer = 0;
+        const uint32_t set_cols = (uint32_t)q.set_cols, Nc = (uint32_t)q.Nc;
+        const uint64_t desc0 = make_desc(0);
+        const uint32_t stage_u = smem_u32(s_stage) >> 4, stage_step = stage_bytes >> 4;     // 16-byte units, as the descriptor counts
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4, bres_u = smem_u32(s_bres) >> 4;
+        const bool merged = PASSES == 3 && q.merge;
+        RingPos sp{0, 0};
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
             const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
             const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;          // how often this accumulator set was used before
             if (use >= 1) mbar_wait_t(&acc_empty[buf], (use - 1) & 1, &w1, rec);  // the epilogue has drained this accumulator set
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            bool corr_started = false;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % q.nstage;
-                mbar_wait_t(&a_full[s], (it / q.nstage) & 1, &w0, rec);
+            const uint32_t d_set = tmem_base + buf * set_cols;
+            const uint32_t d_corr = d_set + (uint32_t)nmain * Nc;             // shared correction accumulator (unmerged mode)
+            uint32_t d_cur = d_set;                                            // main accumulator (or pair) of this K block
+            int m = 0;
+            uint32_t acc_main = 0, acc_corr = q.ncorr ? 0u : 1u;              // 0: the first MMA into the accumulator overwrites it
+            uint32_t bres_kb = bres_u;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = sp.idx;
+                mbar_wait_t(&a_full[s], sp.par, &w0, rec);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t a_hi = smem_u32(s_stage + s * stage_bytes), a_lo = a_hi + a_bytes;
-                    const uint32_t b_hi = q.b_resident ? smem_u32(s_bres) + (uint32_t)kb * 2 * b_bytes : a_hi + 2 * a_bytes;
-                    const uint32_t b_lo = b_hi + b_bytes;
+                    const uint32_t a_u = stage_u + (uint32_t)s * stage_step;
+                    const uint64_t da_hi = desc0 + a_u, da_lo = da_hi + a_step;
+                    const uint64_t db_hi = desc0 + (q.b_resident ? bres_kb : a_u + 2 * a_step), db_lo = db_hi + b_step;
                     const int ksteps = min(MMA_KB, q.Kpad - kb * MMA_KB) >> 3;
-                    const uint32_t d_main = tmem_base + buf * set_cols + (uint32_t)((kb % nmain) * q.Nc);
-                    const uint32_t d_corr = q.ncorr ? tmem_base + buf * set_cols + (uint32_t)(nmain * q.Nc) : d_main;
-                    if (PASSES == 3 && q.merge) {
+                    if (merged) {
                         // pair (main, correction) in adjacent TMEM columns: [B_hi;B_lo] are adjacent panels, so A_hi x both is one
                         // MMA of N = 2*Nc (a third fewer instructions and A_hi is read from shared memory once)
-                        const uint32_t d_pair = tmem_base + buf * set_cols + (uint32_t)((kb % nmain) * 2 * q.Nc);
-                        for (int t = 0; t < ksteps; ++t) {
-                            const uint32_t koff = (uint32_t)t * 32;
-                            umma_tf32(d_pair, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc2, (kb >= nmain || t > 0) ? 1u : 0u);
-                            umma_tf32(d_pair + (uint32_t)q.Nc, make_desc(a_lo + koff), make_desc(b_hi + koff), q.idesc, 1u);
+                        for (int t = 0; t < ksteps; ++t) {                    // 8 tf32 = 32 bytes = 2 descriptor units per k step
+                            umma_tf32(d_cur, da_hi + 2 * t, db_hi + 2 * t, q.idesc2, acc_main | (uint32_t)(t > 0));
+                            umma_tf32(d_cur + Nc, da_lo + 2 * t, db_hi + 2 * t, q.idesc, 1u);
                         }
-                    } else
-                    for (int t = 0; t < ksteps; ++t) {
-                        const uint32_t koff = (uint32_t)t * 32;       // 8 tf32 = 32 bytes along K inside the swizzle atom
-                        umma_tf32(d_main, make_desc(a_hi + koff), make_desc(b_hi + koff), q.idesc, (kb >= nmain || t > 0) ? 1u : 0u);
-                        if (PASSES == 3) {
-                            umma_tf32(d_corr, make_desc(a_hi + koff), make_desc(b_lo + koff), q.idesc, (corr_started || !q.ncorr) ? 1u : 0u);
-                            umma_tf32(d_corr, make_desc(a_lo + koff), make_desc(b_hi + koff), q.idesc, 1u);
-                            corr_started = true;
+                    } else {
+                        for (int t = 0; t < ksteps; ++t) {
+                            umma_tf32(d_cur, da_hi + 2 * t, db_hi + 2 * t, q.idesc, acc_main | (uint32_t)(t > 0));
+                            if (PASSES == 3) {
+                                umma_tf32(q.ncorr ? d_corr : d_cur, da_hi + 2 * t, db_lo + 2 * t, q.idesc, acc_corr);
+                                umma_tf32(q.ncorr ? d_corr : d_cur, da_lo + 2 * t, db_hi + 2 * t, q.idesc, 1u);
+                                acc_corr = 1u;
+                            }
                         }
                     }
                     umma_commit(&a_empty[s]);
                     if (kb == nkb - 1) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
+                sp.advance(q.nstage);
+                bres_kb += 2 * b_step;
+                d_cur += merged ? 2 * Nc : Nc;
+                if (++m == nmain) { m = 0; d_cur = d_set; acc_main = 1u; }    // K blocks go round-robin over the main accumulators
             }
         }
     } else {
         // =============================================== epilogue ==================================================
-        // 8 warps: TMEM lane quadrant = warp % 4, the two warps of a quadrant split the 16-column groups
+        // 8 warps: TMEM lane quadrant = warp % 4, the two warps of a quadrant split the 16-column groups.  Accumulator a of a set sits
+        // at column a * Nc (merged: main0, corr0, main1, ...; unmerged: the mains, then the shared correction accumulator).
         const int lane_grp = warp & 3, col_half = (warp - MMA_EPI_WARP0) >> 2;
         const int row = lane_grp * 32 + lane;
-        const int nused = min(nmain, nkb);
         const int ncol16 = q.Nc >> 4;
         const int c16_mid = (ncol16 + 1) >> 1;
         const int c16_begin = col_half == 0 ? 0 : c16_mid, c16_end = col_half == 0 ? c16_mid : ncol16;
@@ -725,10 +680,12 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
         float* const out_p = q.out;
         const float* const res_p = q.res;
         const int N_all = q.N;
+        const uint32_t HWu = (uint32_t)HW, Ncu = (uint32_t)q.Nc;
         const uint32_t tlane = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         uint32_t titer = 0;
         const uint32_t set_cols = (uint32_t)q.set_cols;
-        const int nacc = q.merge ? 2 * nused : nused + q.ncorr;
+        const int nacc = q.merge ? 2 * nmain : nmain + q.ncorr;
+        const int nfirst = min(16, N_all - (chunk * q.Nc + c16_begin * 16));       // valid columns of this warp's first group
         // residual of this warp's first 16-column group, fetched one tile ahead (right after the previous tile consumed it) so its
         // HBM latency is hidden behind a tile
         float rnext[16];
@@ -736,8 +693,13 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
             const int bn = tile_n / tiles_per_img, pn = (tile_n - bn * tiles_per_img) * MMA_TP + row;
             const bool ok = has_res && tile_n < ntiles && pn < HW && c16_begin < c16_end;
             const float* rp = q.res + ((size_t)bn * q.N + (size_t)chunk * q.Nc + c16_begin * 16) * HW + (ok ? pn : 0);
+            if (ok && nfirst >= 16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rnext[j] = (ok && chunk * q.Nc + c16_begin * 16 + j < q.N) ? rp[(size_t)j * HW] : 0.f;
+                for (int j = 0; j < 16; ++j) rnext[j] = rp[(size_t)HWu * j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) rnext[j] = (ok && j < nfirst) ? rp[(size_t)HWu * j] : 0.f;
+            }
         };
         prefetch_res(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
@@ -753,18 +715,20 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
             for (int c16 = c16_begin; c16 < c16_end; ++c16) {
                 float acc[16];
                 {
+                    // accumulators are added in IEEE fp32 (one at a time: a second set of 16 registers in flight spills)
+                    uint32_t ta = tacc + (uint32_t)(c16 * 16);
                     uint32_t r[16];
-                    tmem_ld16(tacc + (uint32_t)(c16 * 16), r);
+                    tmem_ld16(ta, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
-                }
-                for (int a = 1; a < nacc; ++a) {      // remaining accumulators: (main, correction) pairs or mains then the correction
-                    uint32_t r[16];
-                    tmem_ld16(tacc + (uint32_t)((q.merge || a < nused ? a : nmain) * q.Nc + c16 * 16), r);
-                    tmem_ld_wait();
+                    for (int a = 1; a < nacc; ++a) {
+                        ta += Ncu;
+                        tmem_ld16(ta, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                    }
                 }
                 if (c16 == c16_end - 1) {        // this warp's TMEM reads of the tile are complete: hand the accumulators back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -773,21 +737,21 @@ __global__ void __launch_bounds__(LD ? MMA_THREADS_LD1 : MMA_THREADS, 1) k_pw_mm
                 }
                 const int n0 = chunk * q.Nc + c16 * 16;
                 if (valid) {
-                    const size_t goff = base + (size_t)(c16 * 16) * HW;
+                    const size_t goff = base + (size_t)HWu * (uint32_t)(c16 * 16);
                     const int nvalid = N_all - n0;            // >= 16: whole group, no per-column predicate
                     const bool pre = c16 == c16_begin;
                     if (epi_mode == 0) {
-                        if (nvalid >= 16) epi_group<true, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HW, 16);
-                        else epi_group<false, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HW, nvalid);
+                        if (nvalid >= 16) epi_group<true, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HWu, 16);
+                        else epi_group<false, false, false, false>(acc, out_p + goff, nullptr, nullptr, nullptr, nullptr, rnext, false, res_coef, HWu, nvalid);
                     } else if (epi_mode == 1) {
-                        if (nvalid >= 16) epi_group<true, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HW, 16);
-                        else epi_group<false, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HW, nvalid);
+                        if (nvalid >= 16) epi_group<true, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HWu, 16);
+                        else epi_group<false, true, false, false>(acc, out_p + goff, res_p + goff, nullptr, nullptr, nullptr, rnext, pre, res_coef, HWu, nvalid);
                     } else {
                         const float* bn = has_bias ? q.bias + n0 : nullptr;
                         const float* fm = has_film ? q.film_mul + goff : nullptr;
                         const float* fa = has_film ? q.film_add + goff : nullptr;
                         // generic: null-guarded (rpre is zero when there is no residual)
-                        epi_group<false, true, true, true>(acc, out_p + goff, has_res ? res_p + goff : nullptr, fm, fa, bn, rnext, pre, res_coef, HW, min(nvalid, 16));
+                        epi_group<false, true, true, true>(acc, out_p + goff, has_res ? res_p + goff : nullptr, fm, fa, bn, rnext, pre, res_coef, HWu, min(nvalid, 16));
                     }
                 }
                 // the prefetched residual has been consumed: refill the same registers for the next tile of this CTA
@@ -834,14 +798,12 @@ __global__ void __launch_bounds__(256) k_group_stats(const float* __restrict__ x
 
 struct PwMmaPlan { int resident, nstage, ring; size_t smem; };
 
-static bool pw_mma_plan(int Nc, int nkb, int prologue, bool ring_holds_tile, int ld, PwMmaPlan* out) {
+static bool pw_mma_plan(int Nc, int nkb, int prologue, bool ring_holds_tile, PwMmaPlan* out) {
     const size_t a_bytes = (size_t)MMA_TP * 128, b_bytes = (size_t)Nc * 128;
     const size_t slot = prologue == 2 ? (size_t)MMA_P2_SLOT : (size_t)MMA_SLOT_BYTES * (prologue == 3 ? 2 : 1);
     const size_t misc = 1024 + (6 * MMA_TP + 2 * MMA_MAX_K) * sizeof(float) + (2 * MMA_MAX_RING + 12) * sizeof(uint64_t) + 64;
     const size_t budget = 227 * 1024;
-    // LayerNorm statistics need all K blocks of a tile resident; with the producers' own cp.async ring (ld = 1) one more slot, because
-    // the slot of the K block converted last is refilled only after the next block's barrier
-    const int ring_min = ring_holds_tile ? max(nkb + ld, 2) : 2 + ld;
+    const int ring_min = ring_holds_tile ? max(nkb, 2) : 2;  // LayerNorm statistics need all K blocks of a tile resident
     PwMmaPlan best;
     bool found = false;
     int ns_hi = 2, ns_lo = 1;                 // operand stages; FDN_MMA_NSTAGE pins the count (dev knob, up to 4)
@@ -939,10 +901,7 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     q.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     const int nkb = (q.Kpad + MMA_KB - 1) / MMA_KB;
     PwMmaPlan plan;
-    // raw-ring loader: 1 = 16-byte cp.async issued by the producer warps (default), 0 = per-row TMA bulk copies from loader warps
-    static const int ld_env = getenv("FDN_MMA_LOADER") ? atoi(getenv("FDN_MMA_LOADER")) : 1;
-    const int ld = ld_env ? 1 : 0;
-    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), ld, &plan), "tile does not fit in shared memory");
+    FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), &plan), "tile does not fit in shared memory");
     q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
     // accumulators: one K block (<= 12 accumulations) needs no split; longer K keeps hi*hi and the corrections apart and
     // spreads the K blocks over up to three main accumulators
@@ -953,13 +912,17 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     int set_cols;
     if (q.merge) {
         // (main, correction) pairs; prefer two accumulator sets (epilogue overlaps the next tile) as long as two pairs remain
-        q.nmain = max(1, min(min(3, nkb), 512 / (2 * Nc)));
+        // main accumulators: one up to K = 128 (<= 16 truncating accumulations each), two up to 256, three beyond - every extra
+        // accumulator costs the epilogue a TMEM load and 16 additions per thread and 16-column group
+        const int want = nkb <= 4 ? 1 : (nkb <= 8 ? 2 : 3);
+        q.nmain = max(1, min(min(want, nkb), 512 / (2 * Nc)));
         if (q.nmain > 2 && 2 * (2 * q.nmain * Nc) > 512 && 2 * (2 * 2 * Nc) <= 512) q.nmain = 2;
         q.ncorr = 0;
         set_cols = 2 * q.nmain * Nc;
         q.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * Nc) >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     } else {
-        if (nkb >= 2) q.nmain = max(1, min(min(3, nkb), (512 / Nc) - q.ncorr));
+        const int want = nkb <= 4 ? 1 : (nkb <= 8 ? 2 : 3);
+        if (nkb >= 2) q.nmain = max(1, min(min(want, nkb), (512 / Nc) - q.ncorr));
         set_cols = (q.nmain + q.ncorr) * Nc;
         q.idesc2 = q.idesc;
     }
@@ -986,32 +949,24 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     const int ntiles = fdn_cdiv(HW, MMA_TP) * B;
     const int gx = min(ntiles, max(1, num_sms / nchunks));
     void (*kern)(PwMmaParams) = nullptr;
-    switch ((prologue * 2 + (passes == 3 ? 1 : 0)) * 2 + ld) {
-        case 0: kern = k_pw_mma<0, 1, 0>; break;
-        case 1: kern = k_pw_mma<0, 1, 1>; break;
-        case 2: kern = k_pw_mma<0, 3, 0>; break;
-        case 3: kern = k_pw_mma<0, 3, 1>; break;
-        case 4: kern = k_pw_mma<1, 1, 0>; break;
-        case 5: kern = k_pw_mma<1, 1, 1>; break;
-        case 6: kern = k_pw_mma<1, 3, 0>; break;
-        case 7: kern = k_pw_mma<1, 3, 1>; break;
-        case 8: kern = k_pw_mma<2, 1, 0>; break;
-        case 9: kern = k_pw_mma<2, 1, 1>; break;
-        case 10: kern = k_pw_mma<2, 3, 0>; break;
-        case 11: kern = k_pw_mma<2, 3, 1>; break;
-        case 12: kern = k_pw_mma<3, 1, 0>; break;
-        case 13: kern = k_pw_mma<3, 1, 1>; break;
-        case 14: kern = k_pw_mma<3, 3, 0>; break;
-        default: kern = k_pw_mma<3, 3, 1>; break;
+    switch (prologue * 2 + (passes == 3 ? 1 : 0)) {
+        case 0: kern = k_pw_mma<0, 1>; break;
+        case 1: kern = k_pw_mma<0, 3>; break;
+        case 2: kern = k_pw_mma<1, 1>; break;
+        case 3: kern = k_pw_mma<1, 3>; break;
+        case 4: kern = k_pw_mma<2, 1>; break;
+        case 5: kern = k_pw_mma<2, 3>; break;
+        case 6: kern = k_pw_mma<3, 1>; break;
+        default: kern = k_pw_mma<3, 3>; break;
     }
-    static bool configured[FDN_MAX_DEVICES][16] = {};      // the opt-in is a per-device function attribute
-    const int ki = (prologue * 2 + (passes == 3 ? 1 : 0)) * 2 + ld;
+    static bool configured[FDN_MAX_DEVICES][8] = {};      // the opt-in is a per-device function attribute
+    const int ki = prologue * 2 + (passes == 3 ? 1 : 0);
     if (!configured[dev][ki]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
         configured[dev][ki] = true;
     }
-    kern<<<dim3(gx, nchunks, 1), dim3(ld ? MMA_THREADS_LD1 : MMA_THREADS), plan.smem, st>>>(q);
+    kern<<<dim3(gx, nchunks, 1), dim3(MMA_THREADS), plan.smem, st>>>(q);
     return fdn_check_launch("k_pw_mma");
 #endif
 }

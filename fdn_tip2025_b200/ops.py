@@ -239,3 +239,31 @@ def post_u8hwc(x, img):
     """x [B,3,Hp,Wp] fp32 RGB -> img [B,h,w,3] uint8 BGR: crop, clamp, *255, round (tensor2img, img_util.py:36-98)."""
     b, h, w, _ = img.shape
     _lib.call("fdn_post_f32chw_to_u8hwc", _p(x), _pu8(img), b, h, w, x.shape[2], x.shape[3], _stream())
+
+
+# ------------------------------------------------------------------------------------------------ validation metrics (basicsr/metrics/psnr_ssim.py)
+def _pd(t):
+    _device_ok(t)
+    assert t.dtype == torch.float64 and t.is_contiguous(), "metric results / scratch are contiguous float64"
+    return t.data_ptr()
+
+
+def psnr(img1, img2, crop_border=0, test_y_channel=False):
+    """calculate_psnr (psnr_ssim.py:8-70) per image: img1, img2 [B,C,H,W] fp32 on the device -> float64 [B] on the device."""
+    b, c, h, w = img1.shape
+    assert img2.shape == img1.shape, "Image shapes are different"
+    out = torch.empty(b, dtype=torch.float64, device=img1.device)
+    ws = torch.empty(4 * b, dtype=torch.float64, device=img1.device)
+    _lib.call("fdn_psnr", _p(img1), _p(img2), _pd(out), _pd(ws), b, c, h, w, crop_border, 1 if test_y_channel else 0, _stream())
+    return out
+
+
+def ssim(img1, img2, crop_border=0, test_y_channel=False, ssim3d=True):
+    """calculate_ssim (psnr_ssim.py:243-329) per image, float64 [B] on the device."""
+    b, c, h, w = img1.shape
+    assert img2.shape == img1.shape, "Image shapes are different"
+    mode = 2 if test_y_channel else (0 if ssim3d else 1)
+    out = torch.empty(b, dtype=torch.float64, device=img1.device)
+    ws = torch.empty(4 * b, dtype=torch.float64, device=img1.device)
+    _lib.call("fdn_ssim", _p(img1), _p(img2), _pd(out), _pd(ws), b, c, h, w, crop_border, mode, _stream())
+    return out

@@ -165,6 +165,18 @@ int fdn_gray_mean(const float* x, float* out, int B, int HW, cudaStream_t st);
 int fdn_pre_u8hwc_to_f32chw(const unsigned char* img, float* out, int B, int h, int w, int Hp, int Wp, cudaStream_t st);
 int fdn_post_f32chw_to_u8hwc(const float* x, unsigned char* img, int B, int h, int w, int Hp, int Wp, cudaStream_t st);
 
+/* ---- validation metrics on the device (basicsr/metrics/psnr_ssim.py) ---------------------------------
+ * img1 / img2 [B][C][H][W] fp32 in [0,1] or [0,255] (the reference decides by img1.max() <= 1, psnr_ssim.py:58,317); results are
+ * float64 like numpy's.  ws: caller-owned scratch of 4*B doubles.  crop_border as in the reference.
+ * fdn_psnr: calculate_psnr (psnr_ssim.py:8-70); test_y_channel != 0 compares the BT.601 Y channel (metric_util.py:34-47).
+ * fdn_ssim: calculate_ssim (psnr_ssim.py:243-329); mode 0 = ssim3d=True, the reference's default: 11x11x11 Gaussian over the
+ *   (H, W, C) volume with replicate padding (:143-200); mode 1 = ssim3d=False: per-channel 11x11 Gaussian, valid region (:84-117);
+ *   mode 2 = test_y_channel=True (:202-240). */
+int fdn_psnr(const float* img1, const float* img2, double* psnr, double* ws, int B, int C, int H, int W, int crop_border,
+             int test_y_channel, cudaStream_t st);
+int fdn_ssim(const float* img1, const float* img2, double* ssim, double* ws, int B, int C, int H, int W, int crop_border, int mode,
+             cudaStream_t st);
+
 #ifdef __cplusplus
 }
 #endif

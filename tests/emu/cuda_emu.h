@@ -61,6 +61,26 @@ static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureS
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __constant__ static
+static inline double atomicAdd(double* p, double v) {          // blocks / threads of the emulator may be real host threads
+    unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = __atomic_load_n(q, __ATOMIC_RELAXED), nxt;
+    double cur;
+    do {
+        memcpy(&cur, &old, 8);
+        cur += v;
+        memcpy(&nxt, &cur, 8);
+    } while (!__atomic_compare_exchange_n(q, &old, nxt, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    memcpy(&cur, &old, 8);
+    return cur;
+}
+static inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 #define __align__(n) __attribute__((aligned(n)))
 #define __ldg(p) (*(p))
 #define __fdividef(a, b) ((a) / (b))

@@ -11,8 +11,6 @@ _enabled = False
 def enable():
     global _enabled
     from fdn_tip2025_b200 import _lib, build, ops
-    if _enabled:
-        return
     path = build.build_emu()
     h = _lib._bind(ctypes.CDLL(path))
     assert h.fdn_is_device_build() == 0

@@ -441,3 +441,44 @@ def case_pw_mma(dev, k, n, hw=(16, 24), prologue=0, passes=3, two_src=False, see
         ref = F.conv2d(a, wf[:, :, None, None], bias.float().double()) + res.float().double()
     sync(dev)
     return compare("pw_mma K=%d N=%d pro=%d passes=%d" % (k, n, prologue, passes), out, ref, rel_l2=tol[0], max_rel=tol[1])
+
+
+# ----------------------------------------------------------------------------------------- validation metrics
+def case_metrics(dev, sizes=((48, 64), (33, 47)), golden=None):
+    """fdn_psnr / fdn_ssim against oracle/metrics_oracle.py (float64) on the same float32 frames, every mode; and against the
+    reference's own numbers (tests/golden/metrics_golden.pt) when `golden` is given."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_metrics_golden as G
+    from oracle import metrics_oracle as MO
+
+    def run(a, b, crop):
+        ta = torch.from_numpy(np.stack([a, a[::-1].copy()])).permute(0, 3, 1, 2).float().contiguous()     # batch of two (second flipped)
+        tb = torch.from_numpy(np.stack([b, b[::-1].copy()])).permute(0, 3, 1, 2).float().contiguous()
+        da, db = ta.to(dev), tb.to(dev)
+        got = {"psnr": ops.psnr(da, db, crop), "psnr_y": ops.psnr(da, db, crop, True), "ssim3d": ops.ssim(da, db, crop),
+               "ssim2d": ops.ssim(da, db, crop, ssim3d=False), "ssim_y": ops.ssim(da, db, crop, test_y_channel=True)}
+        sync(dev)
+        return {k: v.cpu().numpy() for k, v in got.items()}, ta, tb
+
+    cases = [(21 + i, h, w, scale, crop) for i, (h, w) in enumerate(sizes) for scale, crop in ((255, 0), (1, 3))]
+    for seed, h, w, scale, crop in cases:
+        a, b = G.image_pair(seed, h, w, scale)
+        got, ta, tb = run(a, b, crop)
+        for i in range(2):
+            a32, b32 = ta[i].permute(1, 2, 0).double().numpy(), tb[i].permute(1, 2, 0).double().numpy()
+            ref = {"psnr": MO.psnr(a32, b32, crop), "psnr_y": MO.psnr(a32, b32, crop, True), "ssim3d": MO.ssim(a32, b32, crop),
+                   "ssim2d": MO.ssim(a32, b32, crop, ssim3d=False), "ssim_y": MO.ssim(a32, b32, crop, test_y_channel=True)}
+            for k in ref:
+                # psnr_y: the reference evaluates the Y-channel mse in float32 (to_y_channel returns float32), the kernel in float64
+                tol = 2e-5 if k == "psnr_y" else 1e-9
+                assert abs(got[k][i] - ref[k]) <= tol * max(1.0, abs(ref[k])), (k, seed, h, w, scale, crop, i, got[k][i], ref[k])
+    if golden is not None:
+        for rec in golden:
+            a, b = G.image_pair(rec["seed"], rec["h"], rec["w"], rec["scale"])
+            got, _, _ = run(a, b, rec["crop"])
+            for k in ("psnr", "psnr_y", "ssim3d", "ssim2d", "ssim_y"):
+                # the reference's _ssim_3d runs its Conv3d in float32 (psnr_ssim.py:178-182): ~1e-6 of noise; [0,1] frames are
+                # rounded to float32 on their way to the device
+                tol = 5e-6 if k in ("ssim3d", "psnr_y") else (2e-6 if rec["scale"] == 1 else 1e-9)
+                assert abs(got[k][0] - rec[k]) <= tol * max(1.0, abs(rec[k])), (k, rec, got[k][0])
