@@ -37,7 +37,7 @@ def build(verbose=False, force=False):
     """Compile every CUDA source for sm_100a into one shared library.  Returns the library path."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     stamp = LIB + ".sha256"
-    digest = _digest(_all_inputs(), " ".join(NVCC_FLAGS) + os.environ.get("FDN_MMA_PROFILE", ""))
+    digest = _digest(_all_inputs(), " ".join(NVCC_FLAGS) + ",".join(SOURCES) + os.environ.get("FDN_MMA_PROFILE", ""))
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
