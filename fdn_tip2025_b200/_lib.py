@@ -51,6 +51,9 @@ SIGNATURES = {
     "fdn_post_f32chw_to_u8hwc": "ppiiiiis",
     "fdn_psnr": "ppppiiiiiis",
     "fdn_ssim": "ppppiiiiiis",
+    "fdn_diff": "pppls",
+    "fdn_reduce_f64": "ppplis",
+    "fdn_down8_bilinear": "ppiiis",
 }
 _CODE = {"p": _P, "i": _I, "l": _L, "f": _F, "s": _P}
 

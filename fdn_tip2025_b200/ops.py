@@ -267,3 +267,20 @@ def ssim(img1, img2, crop_border=0, test_y_channel=False, ssim3d=True):
     ws = torch.empty(4 * b, dtype=torch.float64, device=img1.device)
     _lib.call("fdn_ssim", _p(img1), _p(img2), _pd(out), _pd(ws), b, c, h, w, crop_border, mode, _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ spectral losses (forward)
+def diff(a, b, out):
+    _lib.call("fdn_diff", _p(a), _p(b), _p(out), a.numel(), _stream())
+
+
+def reduce_f64(a, b, mode):
+    """mode 0: sum |a|; mode 1: sum (a - b)^2.  Returns a float64 scalar tensor on the device."""
+    out = torch.empty(1, dtype=torch.float64, device=a.device)
+    _lib.call("fdn_reduce_f64", _p(a), _p(b), _pd(out), a.numel(), mode, _stream())
+    return out
+
+
+def down8_bilinear(x, out):
+    h, w = x.shape[-2:]
+    _lib.call("fdn_down8_bilinear", _p(x), _p(out), x.numel() // (h * w), h, w, _stream())

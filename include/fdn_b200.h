@@ -177,6 +177,13 @@ int fdn_psnr(const float* img1, const float* img2, double* psnr, double* ws, int
 int fdn_ssim(const float* img1, const float* img2, double* ssim, double* ws, int B, int C, int H, int W, int crop_border, int mode,
              cudaStream_t st);
 
+/* ---- training-side spectral losses, forward only (basicsr/models/losses/losses.py:83-115, 764-774) ---
+ * Small kernels around the global FFT: element-wise difference, float64 reductions (mode 0: sum |a|, mode 1: sum (a-b)^2; *out is
+ * zeroed by the call), and nn.Upsample(scale_factor=1/8, 'bilinear', align_corners=False) (losses.py:768). */
+int fdn_diff(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+int fdn_reduce_f64(const float* a, const float* b, double* out, long long n, int mode, cudaStream_t st);
+int fdn_down8_bilinear(const float* in, float* out, int planes, int H, int W, cudaStream_t st);
+
 #ifdef __cplusplus
 }
 #endif
