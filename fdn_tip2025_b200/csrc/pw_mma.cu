@@ -903,26 +903,28 @@ FDN_API int fdn_pw_mma(const float* src0, int c0, const float* src1, int c1, con
     PwMmaPlan plan;
     FDN_REQUIRE(pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats == nullptr), &plan), "tile does not fit in shared memory");
     q.b_resident = plan.resident; q.nstage = plan.nstage; q.ring = plan.ring;
-    // accumulators: one K block (<= 12 accumulations) needs no split; longer K keeps hi*hi and the corrections apart and
-    // spreads the K blocks over up to three main accumulators
+    // Accumulators.  The tensor core truncates its fp32 accumulator after every instruction, so 3xTF32 keeps the large hi*hi sum and
+    // the small corrections in separate TMEM accumulators and spreads long K over several main accumulators, which the epilogue adds
+    // in IEEE fp32 - but only as far as TWO accumulator sets still fit the 512 TMEM columns: without the second set the epilogue of a
+    // tile cannot overlap the MMAs of the next one, which costs far more (L2 / L3 to_hidden ran 1.6x slower than single-pass TF32
+    // for that reason alone) than the ~1e-6 the extra accumulators buy.  One K block (<= 12 accumulations) needs no split at all.
     q.ncorr = (passes == 3 && nkb >= 2) ? 1 : 0;
     q.nmain = 1;
     q.merge = (passes == 3 && nkb >= 2 && 2 * Nc <= 256) ? 1 : 0;
     if (const char* e = getenv("FDN_MMA_MERGE")) q.merge = q.merge && atoi(e) != 0;
+    // main accumulators wanted: one up to K = 128 (<= 16 truncating accumulations each), two up to 256, three beyond - every extra
+    // accumulator costs the epilogue a TMEM load and 16 additions per thread and 16-column group
+    const int want = nkb <= 4 ? 1 : (nkb <= 8 ? 2 : 3);
     int set_cols;
     if (q.merge) {
-        // (main, correction) pairs; prefer two accumulator sets (epilogue overlaps the next tile) as long as two pairs remain
-        // main accumulators: one up to K = 128 (<= 16 truncating accumulations each), two up to 256, three beyond - every extra
-        // accumulator costs the epilogue a TMEM load and 16 additions per thread and 16-column group
-        const int want = nkb <= 4 ? 1 : (nkb <= 8 ? 2 : 3);
-        q.nmain = max(1, min(min(want, nkb), 512 / (2 * Nc)));
-        if (q.nmain > 2 && 2 * (2 * q.nmain * Nc) > 512 && 2 * (2 * 2 * Nc) <= 512) q.nmain = 2;
+        // (main, correction) pairs of 2*Nc columns
+        q.nmain = max(1, min(min(want, nkb), 256 / (2 * Nc)));
         q.ncorr = 0;
         set_cols = 2 * q.nmain * Nc;
         q.idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * Nc) >> 3) << 17) | ((uint32_t)(MMA_TP >> 4) << 24);
     } else {
-        const int want = nkb <= 4 ? 1 : (nkb <= 8 ? 2 : 3);
-        if (nkb >= 2) q.nmain = max(1, min(min(want, nkb), (512 / Nc) - q.ncorr));
+        if (q.ncorr && 2 * Nc > 256) q.ncorr = 0;          // Nc > 128: main and corrections share one accumulator
+        if (nkb >= 2) q.nmain = max(1, min(min(want, nkb), (256 / Nc) - q.ncorr));
         set_cols = (q.nmain + q.ncorr) * Nc;
         q.idesc2 = q.idesc;
     }
