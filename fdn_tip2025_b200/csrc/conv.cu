@@ -439,16 +439,16 @@ __device__ __forceinline__ void dw_row8(const float (&r0)[10], const float (&r1)
 
 // every output row is finished (activation / gate) and stored as soon as its third input row has arrived, so only the rolling
 // input rows are live: ~64 registers for the plain and GELU modes, ~100 for the gate (two input channels in flight)
-template <int MODE, int MINB>
+template <int MODE, int MINB, int ROWS>
 __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                                                     int C, int H, int W, int per_plane) {
     // grid.y = plane (b*C + c): the channel - and with it the 9 or 18 weights - is uniform over the CTA, so the weights live in
     // uniform registers / constant operands instead of 18 vector registers per thread
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // over ceil(H/4)*(W/8)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // over ceil(H/ROWS)*(W/8)
     if (i >= per_plane) return;
     const int W8 = W >> 3;
     const int x0 = (i % W8) * 8;
-    const int y0 = (i / W8) * 4;
+    const int y0 = (i / W8) * ROWS;
     const int c = blockIdx.y % C;
     const long long b = blockIdx.y / C;
     const int ca = MODE == 2 ? (c >> 1) : c, cb = (C + c) >> 1;
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restric
     }
     float* op = out + (((size_t)b * C + c) * H + y0) * W + x0;
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
+    for (int y = 0; y < ROWS; ++y) {
         float o[8];
         dw_row10(pa, H, W, y0 + y + 1, x0, a2);
         dw_row8(a0, a1, a2, ka, o);
@@ -541,14 +541,24 @@ FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int 
     FDN_REQUIRE(fdn_aligned16(in), "in must be 16-byte aligned");
     if (W % 8 == 0 && !getenv("FDN_DWCONV_W4")) {
         FDN_REQUIRE((long long)B * C <= 65535, "too many planes for one launch");
-        const int total8 = ((H + 3) / 4) * (W / 8);
+        // rows per thread: 8 (ten input rows feed eight output rows: 17 % fewer load instructions than 4 rows from six - these kernels
+        // are bound by the LSU issue rate) when the plane still yields enough threads, else 4
+        static const int rows_env = getenv("FDN_DW_ROWS") ? atoi(getenv("FDN_DW_ROWS")) : 8;
+        const int rows = (rows_env == 8 && H % 8 == 0 && (long long)B * C * (H / 8) * (W / 8) >= 148LL * 2048) ? 8 : 4;
+        const int total8 = ((H + rows - 1) / rows) * (W / 8);
         dim3 grid(fdn_cdiv(total8, 128), B * C), block(128);
         static const int gate_occ = getenv("FDN_DW_GATE_OCC") ? atoi(getenv("FDN_DW_GATE_OCC")) : 5;    // 5 CTAs/SM (96 regs): 8.9 vs 10.2 ms at 4
-        if (mode == 0) { auto k = k_dwconv3_w8<0, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
-        else if (mode == 1) { auto k = k_dwconv3_w8<1, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
-        else if (gate_occ == 5) { auto k = k_dwconv3_w8<2, 5>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
-        else if (gate_occ == 6) { auto k = k_dwconv3_w8<2, 6>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
-        else { auto k = k_dwconv3_w8<2, 4>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }
+#define FDN_DW_LAUNCH(M, OCC)                                                                                          \
+    {                                                                                                                  \
+        if (rows == 8) { auto k = k_dwconv3_w8<M, OCC, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); } \
+        else { auto k = k_dwconv3_w8<M, OCC, 4>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }           \
+    }
+        if (mode == 0) FDN_DW_LAUNCH(0, 8)
+        else if (mode == 1) FDN_DW_LAUNCH(1, 8)
+        else if (gate_occ == 5) FDN_DW_LAUNCH(2, 5)
+        else if (gate_occ == 6) FDN_DW_LAUNCH(2, 6)
+        else FDN_DW_LAUNCH(2, 4)
+#undef FDN_DW_LAUNCH
         return fdn_check_launch("k_dwconv3_w8");
     }
     long long total = (long long)B * C * ((H + 3) / 4) * (W / 4);
