@@ -541,9 +541,9 @@ FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int 
     FDN_REQUIRE(fdn_aligned16(in), "in must be 16-byte aligned");
     if (W % 8 == 0 && !getenv("FDN_DWCONV_W4")) {
         FDN_REQUIRE((long long)B * C <= 65535, "too many planes for one launch");
-        // rows per thread: 8 (ten input rows feed eight output rows: 17 % fewer load instructions than 4 rows from six - these kernels
-        // are bound by the LSU issue rate) when the plane still yields enough threads, else 4
-        static const int rows_env = getenv("FDN_DW_ROWS") ? atoi(getenv("FDN_DW_ROWS")) : 8;
+        // rows per thread: 4.  FDN_DW_ROWS=8 (ten input rows feed eight output rows, 17 % fewer load instructions) measured 3 % slower
+        // on the 8-image step (63.8 vs 62.1 ms): the halved thread count costs more latency hiding than the loads save
+        static const int rows_env = getenv("FDN_DW_ROWS") ? atoi(getenv("FDN_DW_ROWS")) : 4;
         const int rows = (rows_env == 8 && H % 8 == 0 && (long long)B * C * (H / 8) * (W / 8) >= 148LL * 2048) ? 8 : 4;
         const int total8 = ((H + rows - 1) / rows) * (W / 8);
         dim3 grid(fdn_cdiv(total8, 128), B * C), block(128);

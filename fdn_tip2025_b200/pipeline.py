@@ -10,10 +10,16 @@ PCIe in either direction (4x fewer bytes than fp32) and every step in between is
 ``variant`` selects what the script passes as ``ratio_i``: the LPNet output itself (lolblur, inference_fdn_lolblur.py:65,71) or
 mean(gray(img)) / LPNet(img) (lolv1, inference_fdn_lolv1.py:57-64).
 """
+import threading
+
 import numpy as np
 import torch
 
 from . import ops
+
+# Graph capture is serialised across host threads: a device-wide synchronisation (the warm-up's, or the one-off upload of an FFT
+# twiddle table) issued by one worker while another captures on the same device is an error (cudaErrorStreamCaptureUnsupported).
+_CAPTURE_LOCK = threading.Lock()
 
 
 def padded_size(h, w, multiple=32):
@@ -57,6 +63,13 @@ class InferencePipeline:
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         entry = self._graphs.get(key)
+        if entry is None:
+            with _CAPTURE_LOCK:
+                entry = self._capture(key, b, h, w)
+        return entry
+
+    def _capture(self, key, b, h, w):
+        entry = None
         if entry is None:
             frames = torch.zeros(b, h, w, 3, dtype=torch.uint8, device=self.device)
             side = torch.cuda.Stream(device=self.device)

@@ -226,8 +226,53 @@ static void bench_stage() {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ 3. legacy mma.sync tf32 rate
+__global__ void __launch_bounds__(256) k_hmma(float* out, int iters) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    uint32_t a[4] = {0x3f800000u + threadIdx.x, 0x3f800000u, 0x3f000000u, 0x3f800000u}, b[2] = {0x3f800000u, 0x3f000000u + threadIdx.x};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+static void bench_hmma() {
+    float* out;
+    CK(cudaMalloc(&out, 148 * 4 * 256 * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 20000;
+    for (int ctas : {1, 2, 4}) {
+        float ms = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
+            k_hmma<<<148 * ctas, 256>>>(out, iters);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        const double mma = 148.0 * ctas * 8 * 8.0 * iters;          // warp-level instructions
+        printf("hmma m16n8k8 tf32, %d CTAs/SM of 8 warps: %8.3f ms  %7.1f TFLOP/s  (%.2f HMMA per cycle per SM at 1.9 GHz)\n", ctas, ms,
+               mma * 2 * 16 * 8 * 8 / ms / 1e9, mma / 148 / (ms * 1e-3 * 1.9e9));
+    }
+    CK(cudaFree(out));
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 'h') { bench_hmma(); return 0; }
     bench_fma();
     bench_stage();
+    bench_hmma();
     return 0;
 }
