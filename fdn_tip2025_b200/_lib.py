@@ -38,6 +38,8 @@ SIGNATURES = {
     "fdn_gamma_curve": "pppfls",
     "fdn_fill_border": "ppiiiis",
     "fdn_conv2d": "ppppipiiiiiiiiiis",
+    "fdn_conv3x3_mma_cn": "i",
+    "fdn_conv3x3_mma": "pppppiiiiis",
     "fdn_film_maps": "pppppiiiis",
     "fdn_convt4s2": "ppppiiiiiis",
     "fdn_dwconv3": "pppiiiiis",

@@ -137,6 +137,16 @@ class _Ctx:
             self.pack[name] = t
         return t
 
+    def packed_conv3(self, key):
+        """Dense 3x3 conv weight packed for the tensor-core kernel (packing.pack_conv3x3)."""
+        name = "mma3x3:" + key
+        t = self.pack.get(name)
+        if t is None:
+            with torch.no_grad():
+                t = packing.pack_conv3x3(self.sd[key])
+            self.pack[name] = t
+        return t
+
     def flat(self, key):
         return self.cached("flat:" + key, lambda: self.sd[key].reshape(self.sd[key].shape[0], -1))
 
@@ -360,12 +370,22 @@ def _fuse(cx, enc, dec, p):
     return out
 
 
+def _conv3x3(cx, x, key, out):
+    """Dense 3x3 conv (stride 1, padding 1, no bias) of the resamplers: tensor-core implicit GEMM (3xTF32) when the channel counts
+    allow it, else the FFMA kernel (also under FDN_B200_GEMM=ffma)."""
+    cout, cin = cx.sd[key].shape[:2]
+    if _gemm_mode() != "ffma" and cin % 8 == 0 and packing.conv3x3_cn(cout):
+        ops.conv3x3_mma(x, cx.packed_conv3(key), out)
+    else:
+        ops.conv2d(x, cx.plain(key), out, pad=1)
+
+
 def _down(cx, x, key):
     b, c, h, w = x.shape
     t = _new(x, b, c, h // 2, w // 2)
     ops.avgpool2(x, t)
     out = _new(x, b, 2 * c, h // 2, w // 2)
-    ops.conv2d(t, cx.plain(key), out, pad=1)
+    _conv3x3(cx, t, key, out)
     return out
 
 
@@ -374,7 +394,7 @@ def _up(cx, x, key):
     t = _new(x, b, c, 2 * h, 2 * w)
     ops.up2_bilinear(x, t)
     out = _new(x, b, c // 2, 2 * h, 2 * w)
-    ops.conv2d(t, cx.plain(key), out, pad=1)
+    _conv3x3(cx, t, key, out)
     return out
 
 

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "fft_global.cu", "patch_spectral.cu", "pointwise.cu", "pw_mma.cu", "conv.cu", "lpnet.cu", "imgio.cu", "metrics.cu", "losses.cu"]
+SOURCES = ["api.cu", "fft_global.cu", "patch_spectral.cu", "pointwise.cu", "pw_mma.cu", "conv.cu", "conv_mma.cu", "lpnet.cu", "imgio.cu", "metrics.cu", "losses.cu"]
 LIB = os.path.join(HERE, "libfdn_b200.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu", "_build")
 EMU_LIB = os.path.join(EMU_DIR, "libfdn_emu.so")

@@ -176,6 +176,12 @@ def conv2d(x, w, out, bias=None, res=None, res_shift=0, stride=1, pad=1, act=0, 
               _stream())
 
 
+def conv3x3_mma(x, wpack, out, bias=None, res=None):
+    """Tensor-core 3x3 conv (stride 1, padding 1); wpack = packing.pack_conv3x3(weight)."""
+    b, cin, h, wd = x.shape
+    _lib.call("fdn_conv3x3_mma", _p(x), _p(wpack), _p(bias), _p(res), _p(out), b, cin, h, wd, out.shape[1], _stream())
+
+
 def film_maps(img, wmul, wadd, omul, oadd):
     b, c, h, w = omul.shape
     _lib.call("fdn_film_maps", _p(img), _p(wmul), _p(wadd), _p(omul), _p(oadd), b, c, h, w, _stream())

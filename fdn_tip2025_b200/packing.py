@@ -64,3 +64,30 @@ def pack_weight(w, grouped_e=None):
         out.append(torch.gather(t, 3, idx))
     packed = torch.stack(out, 2).contiguous()                # [chunk][kb][2][n][8][4]
     return packed.view(-1), n, nc, nchunks
+
+
+# ---------------------------------------------------------------------------------------------------- 3x3 tensor-core conv
+def conv3x3_cn(cout):
+    """Output channels per CTA of csrc/conv_mma.cu (fdn_conv3x3_mma_cn): 32 or 24, whichever divides Cout, else 0."""
+    for c in (32, 24):
+        if cout % c == 0:
+            return c
+    return 0
+
+
+def pack_conv3x3(w):
+    """w [Cout, Cin, 3, 3] -> flat fp32 [Cout/CN][Cin/8][hi, lo][tap][8 channels][COP] (COP = 40, zero padded): the
+    shared-memory image of one 8-channel K chunk of k_conv3x3_mma, so the kernel stages it with a linear copy.
+    hi = tf32(w), lo = tf32(w - hi)."""
+    w = w.detach().float()
+    cout, cin = w.shape[:2]
+    cn = conv3x3_cn(cout)
+    assert cn and cin % 8 == 0 and tuple(w.shape[2:]) == (3, 3)
+    cop = (cn + 31) // 32 * 32 + 8
+    hi = tf32_round(w.contiguous())
+    lo = tf32_round(w - hi)
+    out = torch.zeros(cout // cn, cin // 8, 2, 9, 8, cop, dtype=torch.float32, device=w.device)
+    for hl, t in enumerate((hi, lo)):
+        v = t.reshape(cout // cn, cn, cin // 8, 8, 9)                    # [z][n][chunk][c][tap]
+        out[:, :, hl, :, :, :cn] = v.permute(0, 2, 4, 3, 1)             # [z][chunk][tap][c][n]
+    return out.reshape(-1).contiguous()

@@ -135,6 +135,13 @@ int fdn_fill_border(float* t, const float* value, int planes, int C, int H, int 
  * res is sampled at (y<<res_shift, x<<res_shift) (nearest-downsampled image for the heads). */
 int fdn_conv2d(const float* in, const float* w, const float* bias, const float* res, int res_shift, float* out, int B, int Cin,
                int Hin, int Win, int Cout, int K, int stride, int pad, int act, int head, cudaStream_t st);
+/* Tensor-core 3x3 convolution, stride 1, padding 1, for the Downsample / Upsample bodies (FDN_arch.py:715-734): implicit GEMM on
+ * mma.sync tf32 in 3xTF32 (fp32-level accuracy).  Cin % 8 == 0; Cout a multiple of CN = fdn_conv3x3_mma_cn(Cout) (32 or 24;
+ * 0 = unsupported).  wpack: host-packed weights [Cout/CN][Cin/8][hi,lo][tap][8][40] (packing.pack_conv3x3).
+ * out = conv(in) + bias + res (bias, res optional). */
+int fdn_conv3x3_mma_cn(int Cout);
+int fdn_conv3x3_mma(const float* in, const float* wpack, const float* bias, const float* res, float* out, int B, int Cin, int H, int W,
+                    int Cout, cudaStream_t st);
 /* FCAFFN FiLM maps (FDN_arch.py:423) in one launch: omul / oadd [B][C][H][W] = 3x3 conv (padding 1) of img [B][3][H][W] with the
  * folded kernels wmul / wadd [C][3][3][3] = conv3_x.weight * conv1_x.weight. */
 int fdn_film_maps(const float* img, const float* wmul, const float* wadd, float* omul, float* oadd, int B, int C, int H, int W,

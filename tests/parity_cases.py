@@ -482,3 +482,23 @@ def case_metrics(dev, sizes=((48, 64), (33, 47)), golden=None):
                 # rounded to float32 on their way to the device
                 tol = 5e-6 if k in ("ssim3d", "psnr_y") else (2e-6 if rec["scale"] == 1 else 1e-9)
                 assert abs(got[k][0] - rec[k]) <= tol * max(1.0, abs(rec[k])), (k, rec, got[k][0])
+
+
+def case_conv3x3_mma(dev, shapes=((32, 64, 40, 72), (64, 32, 33, 50), (128, 64, 16, 24), (64, 128, 16, 40), (24, 48, 20, 36), (96, 48, 9, 33),
+                                  (48, 24, 17, 31), (48, 96, 8, 32))):
+    """Tensor-core 3x3 convolution (3xTF32) against torch float64: every channel pairing of the dim-32 and dim-24 resamplers,
+    ragged tiles (H % 8, W % 32 != 0), with and without bias + residual."""
+    from fdn_tip2025_b200 import packing
+    for cin, cout, h, w in shapes:
+        b = 2
+        x, wgt = rnd(b, cin, h, w, seed=cin + h), rnd(cout, cin, 3, 3, seed=cout + w) / (3.0 * cin ** 0.5)
+        bias, res = rnd(cout, seed=3), rnd(b, cout, h, w, seed=4)
+        wp = packing.pack_conv3x3(dev32(wgt, dev))
+        out = torch.empty(b, cout, h, w, device=dev)
+        ops.conv3x3_mma(dev32(x, dev), wp, out)
+        sync(dev)
+        ref = F.conv2d(x.float().double(), wgt.float().double(), padding=1)
+        compare("conv3x3_mma %d->%d %dx%d" % (cin, cout, h, w), out, ref, rel_l2=2e-6, max_rel=8e-6)
+        ops.conv3x3_mma(dev32(x, dev), wp, out, bias=dev32(bias, dev), res=dev32(res, dev))
+        sync(dev)
+        compare("conv3x3_mma bias/res", out, ref + bias.float().double().view(1, -1, 1, 1) + res.float().double(), rel_l2=2e-6, max_rel=8e-6)

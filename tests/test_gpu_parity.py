@@ -38,6 +38,11 @@ def test_conv2d(cuda_dev):
     P.case_conv2d(cuda_dev)
 
 
+def test_conv3x3_tensor_core(cuda_dev):
+    P.case_conv3x3_mma(cuda_dev)
+    P.case_conv3x3_mma(cuda_dev, shapes=((64, 32, 640, 1120),))       # up2_1 at the benchmarked size
+
+
 def test_convt_dw_misc(cuda_dev):
     P.case_convt_dw_misc(cuda_dev)
 
