@@ -437,6 +437,10 @@ __device__ __forceinline__ void dw_row8(const float (&r0)[10], const float (&r1)
     }
 }
 
+// (Packed fp32x2 rows - FFMA2 / FMUL2, two outputs per issue slot, bit-identical - were measured neutral: the register moves that
+// build the odd-aligned operand pairs eat the saved issue slots; 62.6 vs 60.9 ms per 8-image step.  Kept out.)
+#define DW_ROW8 dw_row8
+
 // every output row is finished (activation / gate) and stored as soon as its third input row has arrived, so only the rolling
 // input rows are live: ~64 registers for the plain and GELU modes, ~100 for the gate (two input channels in flight)
 template <int MODE, int MINB, int ROWS>
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restric
     for (int y = 0; y < ROWS; ++y) {
         float o[8];
         dw_row10(pa, H, W, y0 + y + 1, x0, a2);
-        dw_row8(a0, a1, a2, ka, o);
+        DW_ROW8(a0, a1, a2, ka, o);
         if (MODE >= 1) {
 #pragma unroll
             for (int x = 0; x < 8; ++x) o[x] = fdn_gelu(o[x]);
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restric
         if (MODE == 2) {
             float o2[8];
             dw_row10(pb, H, W, y0 + y + 1, x0, b2);
-            dw_row8(b0, b1, b2, kb, o2);
+            DW_ROW8(b0, b1, b2, kb, o2);
 #pragma unroll
             for (int x = 0; x < 8; ++x) o[x] *= o2[x];
 #pragma unroll
@@ -491,6 +495,80 @@ __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restric
         if (y0 + y < H) {
             *reinterpret_cast<float4*>(op + (size_t)y * W) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(op + (size_t)y * W + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
+// Gate mode for a PAIR of output channels (2m, 2m+1): both read input channel m for the GELU branch and input channel (C + 2m) / 2
+// (and (C + 2m + 1) / 2, a different one only when C is odd) for the linear branch, so the rolling input rows are loaded once and
+// feed four convolutions - 12 load/store instructions per 8-pixel row pair instead of 20 with one output channel per thread (these
+// kernels are bound by the LSU issue rate, not by DRAM).  ODD: C is odd, a third set of rows serves output 2m+1.
+template <bool ODD, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_dwgate_pair(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                                                           int C, int H, int W, int per_plane) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                // over ceil(H/4)*(W/8)
+    if (i >= per_plane) return;
+    const int W8 = W >> 3;
+    const int x0 = (i % W8) * 8;
+    const int y0 = (i / W8) * 4;
+    const int npair = (C + 1) >> 1;
+    const int m = blockIdx.y % npair;
+    const long long b = blockIdx.y / npair;
+    const int c0 = 2 * m, c1 = 2 * m + 1;
+    const bool has1 = c1 < C;
+    const int cb0 = (C + c0) >> 1, cb1 = has1 ? (C + c1) >> 1 : cb0;
+    const float* pa = in + ((size_t)b * C + m) * H * W;
+    const float* pb = in + ((size_t)b * C + cb0) * H * W;
+    const float* pd = in + ((size_t)b * C + cb1) * H * W;
+    float ka0[9], ka1[9], kb0[9], kb1[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        ka0[j] = w[c0 * 9 + j];
+        kb0[j] = w[(C + c0) * 9 + j];
+        ka1[j] = has1 ? w[c1 * 9 + j] : 0.f;
+        kb1[j] = has1 ? w[(C + c1) * 9 + j] : 0.f;
+    }
+    float a0[10], a1[10], a2[10], b0[10], b1[10], b2[10], d0[ODD ? 10 : 1], d1[ODD ? 10 : 1], d2[ODD ? 10 : 1];
+    dw_row10(pa, H, W, y0 - 1, x0, a0);
+    dw_row10(pa, H, W, y0, x0, a1);
+    dw_row10(pb, H, W, y0 - 1, x0, b0);
+    dw_row10(pb, H, W, y0, x0, b1);
+    if (ODD) {
+        dw_row10(pd, H, W, y0 - 1, x0, reinterpret_cast<float(&)[10]>(d0));
+        dw_row10(pd, H, W, y0, x0, reinterpret_cast<float(&)[10]>(d1));
+    }
+    float* op0 = out + (((size_t)b * C + c0) * H + y0) * W + x0;
+    float* op1 = out + (((size_t)b * C + c1) * H + y0) * W + x0;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        float g0[8], g1[8], l0[8], l1[8];
+        dw_row10(pa, H, W, y0 + y + 1, x0, a2);
+        dw_row10(pb, H, W, y0 + y + 1, x0, b2);
+        DW_ROW8(a0, a1, a2, ka0, g0);
+        DW_ROW8(a0, a1, a2, ka1, g1);
+        DW_ROW8(b0, b1, b2, kb0, l0);
+        if (ODD) {
+            dw_row10(pd, H, W, y0 + y + 1, x0, reinterpret_cast<float(&)[10]>(d2));
+            DW_ROW8(reinterpret_cast<float(&)[10]>(d0), reinterpret_cast<float(&)[10]>(d1), reinterpret_cast<float(&)[10]>(d2), kb1, l1);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { d0[ODD ? j : 0] = d1[ODD ? j : 0]; d1[ODD ? j : 0] = d2[ODD ? j : 0]; }
+        } else {
+            DW_ROW8(b0, b1, b2, kb1, l1);
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            g0[x] = fdn_gelu(g0[x]) * l0[x];
+            g1[x] = fdn_gelu(g1[x]) * l1[x];
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; b0[j] = b1[j]; b1[j] = b2[j]; }
+        if (y0 + y < H) {
+            *reinterpret_cast<float4*>(op0 + (size_t)y * W) = make_float4(g0[0], g0[1], g0[2], g0[3]);
+            *reinterpret_cast<float4*>(op0 + (size_t)y * W + 4) = make_float4(g0[4], g0[5], g0[6], g0[7]);
+            if (has1) {
+                *reinterpret_cast<float4*>(op1 + (size_t)y * W) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+                *reinterpret_cast<float4*>(op1 + (size_t)y * W + 4) = make_float4(g1[4], g1[5], g1[6], g1[7]);
+            }
         }
     }
 }
@@ -553,6 +631,14 @@ FDN_API int fdn_dwconv3(const float* in, const float* w, float* out, int B, int 
         if (rows == 8) { auto k = k_dwconv3_w8<M, OCC, 8>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); } \
         else { auto k = k_dwconv3_w8<M, OCC, 4>; FDN_LAUNCH_SEQ(k, grid, block, 0, st, in, w, out, C, H, W, total8); }           \
     }
+        static const int pair_env = getenv("FDN_DW_GATE_PAIR") ? atoi(getenv("FDN_DW_GATE_PAIR")) : 1;
+        if (mode == 2 && pair_env) {          // two output channels per thread: the shared input rows are loaded once
+            const int total4 = ((H + 3) / 4) * (W / 8);
+            dim3 pgrid(fdn_cdiv(total4, 128), B * ((C + 1) / 2));
+            if (C & 1) { auto k = k_dwgate_pair<true, 3>; FDN_LAUNCH_SEQ(k, pgrid, block, 0, st, in, w, out, C, H, W, total4); }
+            else { auto k = k_dwgate_pair<false, 4>; FDN_LAUNCH_SEQ(k, pgrid, block, 0, st, in, w, out, C, H, W, total4); }
+            return fdn_check_launch("k_dwgate_pair");
+        }
         if (mode == 0) FDN_DW_LAUNCH(0, 8)
         else if (mode == 1) FDN_DW_LAUNCH(1, 8)
         else if (gate_occ == 5) FDN_DW_LAUNCH(2, 5)
