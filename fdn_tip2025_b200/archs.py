@@ -338,12 +338,30 @@ def _fcaffn(cx, x, side, p):
     return out
 
 
+_NVTX = os.environ.get("FDN_B200_NVTX") == "1"      # NVTX ranges per sub-block (nsys / ncu --nvtx), off by default
+
+
+@contextlib.contextmanager
+def _range(name):
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        yield
+
+
 def _tblock(cx, x, side, p):
     if (p + "attn.fft") in cx.sd:
-        x = _fdsa(cx, x, p)
-    x = _fdffn(cx, x, p)
+        with _range("FDSA " + p):
+            x = _fdsa(cx, x, p)
+    with _range("FDFFN " + p):
+        x = _fdffn(cx, x, p)
     if (p + "ffn2.project_in.weight") in cx.sd:
-        x = _fcaffn(cx, x, side, p)
+        with _range("FCAFFN " + p):
+            x = _fcaffn(cx, x, side, p)
     return x
 
 
@@ -573,10 +591,14 @@ def _spectral_map(cx, x, norm_p, mode):
 def _fdn(cx, img, ratio, variant):
     pyr = _pyramid(img)
     norms = ("norm1.", "norm2.", "norm3.")
-    pha = [_spectral_map(cx, t, n, ops.COLS_FWD_ANGLE) for t, n in zip(pyr, norms)]
-    q3, q2, q1 = _mar(cx, img, ratio, "net_a.", variant, True, pyr)
-    amp = [_spectral_map(cx, t, n, ops.COLS_FWD_ABS) for t, n in zip((q1, q2, q3), norms)]
-    out = _fdformer(cx, img, (amp[0], pha[0], q1), (amp[1], pha[1], q2), (amp[2], pha[2], q3), "net_p.")
+    with _range("FDN prologue (phase maps)"):
+        pha = [_spectral_map(cx, t, n, ops.COLS_FWD_ANGLE) for t, n in zip(pyr, norms)]
+    with _range("MAR"):
+        q3, q2, q1 = _mar(cx, img, ratio, "net_a.", variant, True, pyr)
+    with _range("FDN prologue (amplitude maps)"):
+        amp = [_spectral_map(cx, t, n, ops.COLS_FWD_ABS) for t, n in zip((q1, q2, q3), norms)]
+    with _range("FDformer"):
+        out = _fdformer(cx, img, (amp[0], pha[0], q1), (amp[1], pha[1], q2), (amp[2], pha[2], q3), "net_p.")
     return out, q1, q2, q3
 
 
