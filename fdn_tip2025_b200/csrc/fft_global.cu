@@ -146,23 +146,39 @@ __device__ __forceinline__ void butterfly(float2 v[R]) {
         fft8_c2c<SGN>(v);
     }
 }
+// Odd-length DFT (R in {3,5,7}) through the conjugate-pair symmetry of the roots: with a_n = v[n] + v[R-n], b_n = v[n] - v[R-n],
+//   X[k] = v[0] + sum_n a_n cos(2 pi n k / R) + i SGN sum_n b_n sin(2 pi n k / R),   X[R-k] = the same with -i,
+// i.e. 2 (R-1) real FMAs per output PAIR instead of 4 (R-1) per output for the plain sum (radix 7: 9 operations per output, was 24 -
+// the radix-7 / radix-10 passes were the most expensive part of the row transforms).
 template <int R, int SGN>
-__device__ __forceinline__ void butterfly_direct(float2 v[R]) {   // R in {3,5,7}
-    float2 o[R];
+__device__ __forceinline__ void butterfly_direct(float2 v[R]) {
+    constexpr int Hf = (R - 1) / 2;
+    float2 a[Hf], b[Hf];
+    float2 sum = v[0];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float2 acc = v[0];
-#pragma unroll
-        for (int s = 1; s < R; ++s) {
-            const int k = (r * s) % R;
-            const float wc = Roots<R>::c(k), ws = SGN * Roots<R>::s(k);   // e^{SGN 2 pi i k / R}
-            acc.x += v[s].x * wc - v[s].y * ws;
-            acc.y += v[s].x * ws + v[s].y * wc;
-        }
-        o[r] = acc;
+    for (int n = 1; n <= Hf; ++n) {
+        a[n - 1] = cadd(v[n], v[R - n]);
+        b[n - 1] = csub(v[n], v[R - n]);
+        sum = cadd(sum, a[n - 1]);
     }
+    const float2 v0 = v[0];
+    v[0] = sum;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = o[r];
+    for (int k = 1; k <= Hf; ++k) {
+        float2 A = v0, B = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 1; n <= Hf; ++n) {
+            const int m = (n * k) % R;
+            const float wc = Roots<R>::c(m), ws = Roots<R>::s(m);
+            A.x = fmaf(a[n - 1].x, wc, A.x);
+            A.y = fmaf(a[n - 1].y, wc, A.y);
+            B.x = fmaf(b[n - 1].x, ws, B.x);
+            B.y = fmaf(b[n - 1].y, ws, B.y);
+        }
+        // X[k] = A + i SGN B, X[R-k] = A - i SGN B
+        v[k] = make_float2(A.x - SGN * B.y, A.y + SGN * B.x);
+        v[R - k] = make_float2(A.x + SGN * B.y, A.y - SGN * B.x);
+    }
 }
 
 // exact n / d for 0 <= n < 2^22 with rcp = 1.0f / d (one multiply instead of an integer division)
