@@ -80,7 +80,9 @@ class InferencePipeline:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="relaxed"):    # kernel-attribute calls of the C ABI are not stream work
+            # an explicit capture stream on THIS device: torch.cuda.graph's default capture stream is created once per process, on
+            # whichever device was current first, and kernels captured on another GPU's stream fault
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="relaxed"):    # kernel-attribute calls of the C ABI are not stream work
                 out, ratio = self.run_device(frames)
             entry = (graph, frames, out, ratio)
             self._graphs[key] = entry
