@@ -129,6 +129,8 @@ template <> struct Roots<7> {
     }
 };
 
+#include "fft_roots.cuh"      // Roots<11>, <13>, <17>, <19>
+
 template <int R, int SGN>
 __device__ __forceinline__ void butterfly(float2 v[R]) {
     if constexpr (R == 2) {
@@ -203,7 +205,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 #pragma unroll
             for (int r = 1; r < R; ++r) v[r] = tw_mul<SGN>(v[r], P.tw[r * k * M]);
         }
-        if constexpr (R == 3 || R == 5 || R == 7) butterfly_direct<R, SGN>(v); else butterfly<R, SGN>(v);
+        if constexpr (R % 2 == 1) butterfly_direct<R, SGN>(v); else butterfly<R, SGN>(v);
         float2* dst = out + seq * ss;
         if (!COLS && Ns == 1 && (R % 2 == 0)) {
             // first pass of a row transform: the R outputs of a butterfly are contiguous -> 128-bit conflict-free stores
@@ -226,37 +228,51 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
     }
 }
 
-// Any other prime radix: one thread per output element, direct sum over the R inputs.
+// Any other odd prime radix (23, 61, 107, 281, ...): one thread per output PAIR (r, R - r) of a butterfly.  With the butterfly's twiddled
+// inputs y[q] = x[q] w^{q k M}, a_q = y[q] + y[R-q], b_q = y[q] - y[R-q]:
+//   Y[r] = y[0] + sum_{q=1..h} a_q cos(2 pi q r / R) + i SGN sum_q b_q sin(2 pi q r / R),   Y[R-r] = the same with -i        (h = (R-1)/2)
+// - half the terms of the plain sum and two outputs from them.  The R roots come from the length-N table at stride N / R.
 template <int SGN, bool COLS>
 __device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
                                                       int R, int Ns, int nseq, int ss, int es, int lg) {
-    const int N = P.N, NR = N / R, M = N / (Ns * R);
-    const float rcpNs = 1.0f / (float)Ns, rcpR = 1.0f / (float)R;
-    auto one = [&](int seq, int o) {
-        const int oh = fast_div(o, rcpNs), k = o - oh * Ns;          // o = (jhi*R + r)*Ns + k
-        const int jhi = fast_div(oh, rcpR), r = oh - jhi * R;
-        const int j = jhi * Ns + k;
-        const int step = (k + r * Ns) * M;     // < N
-        const float2* src = in + seq * ss;
-        float2 acc = make_float2(0.f, 0.f);
-        int t = 0;
-        for (int q = 0; q < R; ++q) {
-            float2 x = src[(j + q * NR) * es];
-            float2 pr = tw_mul<SGN>(x, P.tw[t]);
-            acc.x += pr.x;
-            acc.y += pr.y;
-            t += step;
-            if (t >= N) t -= N;
+    const int N = P.N, NR = N / R, M = N / (Ns * R), NRs = N / R;      // NRs: stride of the R-th roots in the table
+    const int h = (R - 1) >> 1, npair = h + 1;                          // pair 0 = output 0 alone
+    const float rcpNs = 1.0f / (float)Ns, rcpP = 1.0f / (float)npair;
+    auto one = [&](int seq, int o) {                                    // o = j * npair + r,  j = butterfly (jhi * Ns + k)
+        const int j = fast_div(o, rcpP), r = o - j * npair;
+        const int jhi = fast_div(j, rcpNs), k = j - jhi * Ns;
+        const float2* src = in + seq * ss + j * es;
+        const int tstep = k * M;                                        // input twiddle exponent step: y[q] = x[q] w_N^{q k M}
+        const int rstep = r * NRs;                                      // root exponent step: w_R^{q r} = w_N^{q r N / R}
+        const float2 y0 = src[0];
+        float2 A = y0, B = make_float2(0.f, 0.f);
+        int tq = 0, tRq = 0, rq = 0;                                    // exponents of y[q], y[R-q] twiddles and of the root, mod N
+        // y[R-q] twiddle exponent (R-q) k M = R k M - q k M = (N / Ns) k - q k M  (mod N)
+        const int tR0 = (int)(((long long)(N / Ns) * k) % N);
+        for (int q = 1; q <= h; ++q) {
+            tq += tstep; if (tq >= N) tq -= N;
+            rq += rstep; if (rq >= N) rq -= N;
+            tRq = tR0 - tq; if (tRq < 0) tRq += N;
+            const float2 yq = tw_mul<SGN>(src[(size_t)q * NR * es], P.tw[tq]);
+            const float2 yr = tw_mul<SGN>(src[(size_t)(R - q) * NR * es], P.tw[tRq]);
+            const float2 w = P.tw[rq];                                  // (cos, -sin) of 2 pi q r / R
+            A.x = fmaf(yq.x + yr.x, w.x, A.x);
+            A.y = fmaf(yq.y + yr.y, w.x, A.y);
+            B.x = fmaf(yq.x - yr.x, -w.y, B.x);
+            B.y = fmaf(yq.y - yr.y, -w.y, B.y);
         }
-        out[seq * ss + o * es] = acc;
+        float2* dst = out + seq * ss;
+        const int o0 = (jhi * R) * Ns + k;                              // output r of the butterfly lives at (jhi * R + r) * Ns + k
+        dst[(size_t)(o0 + r * Ns) * es] = make_float2(A.x - SGN * B.y, A.y + SGN * B.x);
+        if (r > 0) dst[(size_t)(o0 + (R - r) * Ns) * es] = make_float2(A.x + SGN * B.y, A.y - SGN * B.x);
     };
     if (COLS) {
-        const int total = N << lg;
+        const int total = (NR * npair) << lg;
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) one(idx & (nseq - 1), idx >> lg);
     } else {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         for (int seq = warp; seq < nseq; seq += nwarps)
-            for (int o = lane; o < N; o += 32) one(seq, o);
+            for (int o = lane; o < NR * npair; o += 32) one(seq, o);
     }
 }
 
@@ -276,6 +292,11 @@ __device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq,
             case 5: stockham_pass<5, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
             case 7: stockham_pass<7, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
             case 8: stockham_pass<8, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            // unrolled odd radices of the 608x416 (13, 19), 3840x2176 (17) and fourier_fuse (11, 17, 19) transforms
+            case 11: stockham_pass<11, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 13: stockham_pass<13, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 17: stockham_pass<17, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
+            case 19: stockham_pass<19, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
             default: stockham_pass_generic<SGN, COLS>(a, b, P, R, Ns, nseq, ss, es, lg); break;
         }
         __syncthreads();

@@ -25,7 +25,7 @@ def emu():
     importlib.reload(ops)
 
 
-@pytest.mark.parametrize("h,w", [(8, 8), (16, 24), (30, 14), (13, 22), (34, 26)])
+@pytest.mark.parametrize("h,w", [(8, 8), (16, 24), (30, 14), (13, 22), (34, 26), (46, 58), (23, 62)])
 def test_emu_fft(emu, h, w):
     P.case_rfft2_irfft2(emu, h, w)
     P.case_irfft2_nonhermitian(emu, h, w)
