@@ -29,6 +29,7 @@ SIGNATURES = {
     "fdn_pw_conv": "piipiipiippppipppfpplliiiiis",
     "fdn_has_tcgen05": "",
     "fdn_pw_mma_set_debug": "p",
+    "fdn_pw_mma_supported": "iiii",
     "fdn_pw_mma": "pipipiiiippplpppppfpiiis",
     "fdn_group_stats": "ppiiiis",
     "fdn_chan_ln": "ppppplpliiiis",

@@ -237,17 +237,23 @@ def _gemm_mode():
     return mode
 
 
-MMA_MAX_K = 512      # csrc/pw_mma.cu: LayerNorm gamma/beta staging; wider layers (FDformer dim 48 at level 3) run on k_pw_conv
+_MMA_OK = {}
 
 
-def _mma_ok(k):
-    return k <= MMA_MAX_K
+def _mma_ok(k, n, prologue=0, stats_in_kernel=False):
+    """Layers the tensor-core kernel cannot hold (K > 512, or a tile that does not fit in shared memory: FDformer dim 48 at level 3)
+    run on the CUDA-core GEMM kernel of the same library - never on anything else."""
+    key = (k, n, prologue, stats_in_kernel)
+    ok = _MMA_OK.get(key)
+    if ok is None:
+        ok = _MMA_OK[key] = ops.pw_mma_supported(k, n, prologue, stats_in_kernel)
+    return ok
 
 
 def _conv1x1(cx, srcs, key, out, ln=None, bias=None, film=None, res=None):
     """1x1 convolution of the FDformer blocks: tcgen05 kernel, or the FFMA kernel when FDN_B200_GEMM=ffma."""
     mode = _gemm_mode()
-    if mode == "ffma" or not _mma_ok(sum(t.shape[1] for t in srcs)):
+    if mode == "ffma" or not _mma_ok(sum(t.shape[1] for t in srcs), out.shape[1], 1 if ln else 0):
         ops.pw_conv([(t, 0) for t in srcs], cx.wt(key), out, bias=bias, ln=ln, film=film, res=res, res_coef=1.0)
     else:
         ops.pw_mma(srcs, cx.packed(key), out, prologue=1 if ln else 0, ln=ln, bias=bias, film=film, res=res, res_coef=1.0,
@@ -267,7 +273,8 @@ def _fdsa(cx, x, p):
     g3, b3 = cx.ln3(p + "attn.")
     out = _new(x, b, c, h, w)
     mode = _gemm_mode()
-    if mode == "ffma" or not _mma_ok(3 * e):
+    in_kernel = not (e > 40 or os.environ.get("FDN_B200_GATE_STATS") == "prepass")
+    if mode == "ffma" or not _mma_ok(3 * e, c, 2, in_kernel):
         ops.chan_ln(o, o, g3, b3, groups=3, mul=vv, mul_bs=e * h * w)
         ops.pw_conv([(o, 0)], cx.wt(p + "attn.project_out.weight"), out, res=x, res_coef=1.0)
     else:   # norm1..3, the v_value gate and project_out in one kernel.  LayerNorm statistics: computed by the kernel's producers when
@@ -325,7 +332,7 @@ def _fcaffn(cx, x, side, p):
     ops.film_maps(img, cx.film(p + "ffn2.", "mul"), cx.film(p + "ffn2.", "add"), fmul, fadd)
     t = _new(x, b, c, h, w)
     mode = _gemm_mode()
-    if mode == "ffma" or not _mma_ok(c):
+    if mode == "ffma" or not _mma_ok(c, c, 3):
         g, bt = cx.ln(p + "ffn2.norm.")
         ops.chan_ln(y, y, g, bt, mul=x1, mul_bs=c * h * w, add=x1, add_bs=c * h * w)
         ops.pw_conv([(y, 0)], cx.wt(p + "ffn2.project_in.weight"), t, film=(fmul, fadd))
@@ -381,7 +388,7 @@ def _fuse(cx, enc, dec, p):
     wt, bias = cx.fuse_out(p)
     out = _new(enc, b, n, h, w)
     mode = _gemm_mode()
-    if mode == "ffma" or not _mma_ok(2 * n):
+    if mode == "ffma" or not _mma_ok(2 * n, n, 0):
         ops.pw_conv([(x, 0)], wt, out, bias=bias)
     else:
         ops.pw_mma([x], cx.packed_fuse_out(p), out, bias=bias, passes=1 if mode == "tf32" else 3)

@@ -846,6 +846,22 @@ FDN_API int fdn_has_tcgen05() {
 #endif
 }
 
+// 1 if fdn_pw_mma can run a layer with K input channels (prologue 2: K = 3E), output chunks of Nc columns and the given prologue
+// (stats_in_kernel: prologue 2 without a statistics pre-pass); 0 if its tile does not fit in shared memory or K exceeds the
+// LayerNorm staging (callers then use fdn_pw_conv).  Pure host arithmetic.
+FDN_API int fdn_pw_mma_supported(int K, int Nc, int prologue, int stats_in_kernel) {
+#ifdef FDN_EMU
+    return 0;
+#else
+    if (K <= 0 || K > MMA_MAX_K || Nc < 16 || Nc > 256 || (Nc & 15) || prologue < 0 || prologue > 3) return 0;
+    const int Kpad = prologue == 2 ? ((K / 3 + MMA_EB - 1) / MMA_EB) * MMA_KB : ((K + 7) & ~7);
+    const int nkb = (Kpad + MMA_KB - 1) / MMA_KB;
+    if (nkb * MMA_KB > 1024) return 0;
+    PwMmaPlan plan;
+    return pw_mma_plan(Nc, nkb, prologue, prologue == 1 || prologue == 3 || (prologue == 2 && stats_in_kernel), &plan) ? 1 : 0;
+#endif
+}
+
 // stats[b][g][0][p] = mean over the C channels of group g, stats[b][g][1][p] = 1/sqrt(biased var + 1e-5); x [B][G*C][HW]
 FDN_API int fdn_group_stats(const float* x, float* stats, int B, int G, int C, int HW, cudaStream_t st) {
 #ifdef FDN_EMU

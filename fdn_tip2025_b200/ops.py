@@ -122,6 +122,13 @@ def has_tcgen05():
     return _lib.load().fdn_has_tcgen05() == 1
 
 
+def pw_mma_supported(k, n, prologue=0, stats_in_kernel=False):
+    """Whether the tensor-core 1x1 kernel can run a layer with k inputs and n outputs (shared-memory plan, K limit)."""
+    from . import packing
+    nc, _ = packing.chunking(n)
+    return _lib.load().fdn_pw_mma_supported(int(k), int(nc), int(prologue), 1 if stats_in_kernel else 0) == 1
+
+
 def pw_mma(srcs, packed, out, prologue=0, ln=None, aux=None, aux_bs=0, stats=None, bias=None, film=None, res=None, res_coef=1.0, passes=3):
     """srcs: one or two [B,C,H,W] tensors (channel concat); packed = packing.pack_weight(w) on the same device."""
     bpack, n, nc, nchunks = packed

@@ -102,6 +102,9 @@ int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1, int c1
  * (statistics = fdn_group_stats output, or NULL to have the kernel compute them - allowed while K/3 <= 40) times v_value=aux (FDN_arch.py:633-639), 3 FCAFFN mix LN(src)*aux + aux (FDN_arch.py:420).  Epilogue: +bias,
  * *film_mul+film_add, +res_coef*res.  passes: 3 = 3xTF32 split (fp32-level accuracy), 1 = single TF32. */
 int fdn_has_tcgen05(void);
+/* 1 if fdn_pw_mma supports a layer with K inputs (prologue 2: K = 3E), chunks of Nc output columns and this prologue
+ * (stats_in_kernel: prologue 2 with stats == NULL); 0 = tile does not fit in shared memory / K too wide: use fdn_pw_conv. */
+int fdn_pw_mma_supported(int K, int Nc, int prologue, int stats_in_kernel);
 /* Development aid: 8 uint64 device counters receiving the per-role barrier wait cycles of following fdn_pw_mma launches (NULL = off).
  * Counting is compiled in only with -DFDN_MMA_PROFILE=1 (FDN_MMA_PROFILE=1 python -m fdn_tip2025_b200.build); otherwise a no-op. */
 int fdn_pw_mma_set_debug(void* counters);

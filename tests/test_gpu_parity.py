@@ -203,6 +203,39 @@ def test_reference_module_paths_resolve(cuda_dev):
     assert len(out) == 4 and out[0].shape == x.shape
 
 
+@pytest.mark.parametrize("dim", [48, 32])
+def test_fdformer_standalone(cuda_dev, dim):
+    """The stand-alone FDformer module (FDN_arch.py:753-842) with its reference default dim = 48 (level-3 layers wider than the
+    tensor-core kernel's K limit run on the CUDA-core GEMM) and with dim = 32, side maps supplied by the caller, vs the fp64 oracle."""
+    from fdn_tip2025_b200 import archs, schema, synth
+    table = schema.fdformer_schema(dim)
+    sd = synth.make_state_dict(table, seed=9)
+    for k in sd:                                            # damp the residual branches like the FDN fixtures
+        if k.endswith("project_out.weight"):
+            sd[k] = sd[k] * 0.005
+    net = archs.FDformer(dim=dim)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_dev).eval()
+    b, h, w = 1, 64, 96
+    img = synth.low_light_images(b, h, w)
+    sides, sides64 = [], []
+    for lvl in range(3):
+        hl, wl = h >> lvl, w >> lvl
+        amp = P.rnd(b, 3, hl, wl // 2 + 1, seed=lvl + 1).abs() * 3
+        pha = P.rnd(b, 3, hl, wl // 2 + 1, seed=lvl + 4) * 3.14
+        im = P.rnd(b, 3, hl, wl, seed=lvl + 7).abs()
+        sides.append(tuple(P.dev32(t, cuda_dev) for t in (amp, pha, im)))
+        sides64.append(tuple(t.float().double() for t in (amp, pha, im)))
+    got = net(img.to(cuda_dev), x_high1=sides[0][0], x_high12=sides[0][1], x1=sides[0][2], x_high2=sides[1][0], x_high22=sides[1][1],
+              x2=sides[1][2], x_high3=sides[2][0], x_high32=sides[2][1], x3=sides[2][2])
+    ref = P.O.fdformer(img.double(), sides64[0], sides64[1], sides64[2], P._sd64(sd), p="")
+    d = (got.double().cpu() - ref).abs().max().item()
+    assert d <= 1e-3 and P.O.psnr(got.cpu(), ref) >= 50.0, (dim, d)
+    with pytest.raises(RuntimeError):                       # side maps are validated (shape, device)
+        net(img.to(cuda_dev), x_high1=sides[1][0], x_high12=sides[0][1], x1=sides[0][2], x_high2=sides[1][0], x_high22=sides[1][1],
+            x2=sides[1][2], x_high3=sides[2][0], x_high32=sides[2][1], x3=sides[2][2])
+
+
 def _golden_replay(cuda_dev, strict):
     path = os.path.join(GOLDEN, "fdn_golden_strict.pt" if strict else "fdn_golden.pt")
     if not os.path.exists(path):
