@@ -80,5 +80,30 @@ __device__ __forceinline__ float fdn_act(float v, int act) {
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+// Complex add / subtract / multiply-by-a-real on Blackwell's packed fp32x2 pipe (FADD2 / FFMA2: one issue slot for both halves of a
+// float2 that sits in an aligned register pair, which is how LDS.64 / LDG.64 and other packed results deliver it).  IEEE round-to-nearest
+// per half, no FTZ: bit-identical to the scalar forms, which the emulation build keeps.  The FFT butterflies are mostly these.
+#ifdef FDN_EMU
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cfma(float2 a, float s, float2 c) { return make_float2(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y)); }   // a*s + c
+#else
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 cfma(float2 a, float s, float2 c) {   // a*s + c
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mov.b64 rc, {%5, %6}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+    return r;
+}
+#endif

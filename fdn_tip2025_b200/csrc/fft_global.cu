@@ -57,14 +57,17 @@ static int fdn_fft_get_plan(int N, FftPlanDev* out, cudaStream_t st = nullptr) {
     p.N = N;
     p.npass = 0;
     int n = N;
-    const int pref[] = {8, 4, 2, 3, 5, 7};
+    // Prime factors without an unrolled butterfly (23, 107, 281, ... of the fourier_fuse sizes) take the O(p^2) pass; they go FIRST:
+    // the first Stockham pass has no input twiddles (Ns = 1), which is what makes stockham_pass_prime_first cheap.
+    int small[FDN_FFT_MAX_PASSES], nsmall = 0;
+    const int pref[] = {8, 4, 2, 3, 5, 7, 11, 13, 17, 19};
     for (int r : pref)
         while (n % r == 0 && n > 1) {
-            if (p.npass >= FDN_FFT_MAX_PASSES) return -1;
-            p.radix[p.npass++] = r;
+            if (nsmall >= FDN_FFT_MAX_PASSES) return -1;
+            small[nsmall++] = r;
             n /= r;
         }
-    for (int f = 11; n > 1; f += 2) {
+    for (int f = 23; n > 1; f += 2) {
         if (f * f > n) f = n;
         while (n % f == 0) {
             if (p.npass >= FDN_FFT_MAX_PASSES) return -1;
@@ -72,6 +75,8 @@ static int fdn_fft_get_plan(int N, FftPlanDev* out, cudaStream_t st = nullptr) {
             n /= f;
         }
     }
+    if (p.npass + nsmall > FDN_FFT_MAX_PASSES) return -1;
+    for (int i = 0; i < nsmall; ++i) p.radix[p.npass++] = small[i];
     std::vector<float2> tw(N);
     for (int k = 0; k < N; ++k) {
         // exact values on the axes so purely real paths stay exactly real
@@ -155,12 +160,12 @@ __device__ __forceinline__ void butterfly(float2 v[R]) {
 template <int R, int SGN>
 __device__ __forceinline__ void butterfly_direct(float2 v[R]) {
     constexpr int Hf = (R - 1) / 2;
-    float2 a[Hf], b[Hf];
-    float2 sum = v[0];
+    float2 a[Hf], ib[Hf];                     // ib_n = i b_n = (-b_n.y, b_n.x): formed by the subtraction itself, so everything after it is
+    float2 sum = v[0];                        // a complex * real FMA or a complex add (packed FFMA2 / FADD2)
 #pragma unroll
     for (int n = 1; n <= Hf; ++n) {
         a[n - 1] = cadd(v[n], v[R - n]);
-        b[n - 1] = csub(v[n], v[R - n]);
+        ib[n - 1] = make_float2(v[R - n].y - v[n].y, v[n].x - v[R - n].x);
         sum = cadd(sum, a[n - 1]);
     }
     const float2 v0 = v[0];
@@ -171,15 +176,12 @@ __device__ __forceinline__ void butterfly_direct(float2 v[R]) {
 #pragma unroll
         for (int n = 1; n <= Hf; ++n) {
             const int m = (n * k) % R;
-            const float wc = Roots<R>::c(m), ws = Roots<R>::s(m);
-            A.x = fmaf(a[n - 1].x, wc, A.x);
-            A.y = fmaf(a[n - 1].y, wc, A.y);
-            B.x = fmaf(b[n - 1].x, ws, B.x);
-            B.y = fmaf(b[n - 1].y, ws, B.y);
+            A = cfma(a[n - 1], Roots<R>::c(m), A);
+            B = cfma(ib[n - 1], Roots<R>::s(m), B);
         }
-        // X[k] = A + i SGN B, X[R-k] = A - i SGN B
-        v[k] = make_float2(A.x - SGN * B.y, A.y + SGN * B.x);
-        v[R - k] = make_float2(A.x + SGN * B.y, A.y - SGN * B.x);
+        // X[k] = A + SGN i B_plain = A + SGN B,  X[R-k] = A - SGN B
+        v[k] = SGN > 0 ? cadd(A, B) : csub(A, B);
+        v[R - k] = SGN > 0 ? csub(A, B) : cadd(A, B);
     }
 }
 
@@ -276,6 +278,64 @@ __device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__
     }
 }
 
+// The same prime-radix butterfly as the FIRST pass of a transform (Ns = 1: no input twiddles, butterfly j reads x[j + q N/R] and writes
+// X[j R + r]).  A thread produces G output pairs from one sweep over the inputs, so an input pair is read once per G outputs and
+// the inner loop is one root lookup + four FMAs per output pair (the general pass above: two twiddle products and three table
+// reads per term).  Work items are ordered (group, butterfly[, column]) so that lanes read consecutive inputs and the same root.
+template <int SGN, bool COLS, int G>
+__device__ __forceinline__ void stockham_pass_prime_first(const float2* __restrict__ in, float2* __restrict__ out, const FftPlanDev& P,
+                                                          int R, int nseq, int ss, int es, int lg) {
+    const int N = P.N, NR = N / R;                                      // NR butterflies; the R-th roots sit at stride NR in the table
+    const int h = (R - 1) >> 1, npair = h + 1, ngrp = (npair + G - 1) / G;
+    const float rcpNR = 1.0f / (float)NR;
+    auto one = [&](int seq, int o) {                                    // o = g * NR + j
+        const int g = fast_div(o, rcpNR), j = o - g * NR;
+        const float2* src = in + seq * ss + j * es;
+        int rq[G], rstep[G];
+        float2 A[G], B[G];
+        const float2 y0 = src[0];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int r = min(g * G + i, h);
+            rstep[i] = r * NR;
+            rq[i] = 0;
+            A[i] = y0;
+            B[i] = make_float2(0.f, 0.f);
+        }
+        for (int q = 1; q <= h; ++q) {
+            const float2 yq = src[(size_t)q * NR * es], yr = src[(size_t)(R - q) * NR * es];
+            const float2 a = cadd(yq, yr), b = csub(yq, yr);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                rq[i] += rstep[i];
+                if (rq[i] >= N) rq[i] -= N;
+                const float2 w = P.tw[rq[i]];                           // (cos, -sin) of 2 pi q r / R
+                A[i].x = fmaf(a.x, w.x, A[i].x);
+                A[i].y = fmaf(a.y, w.x, A[i].y);
+                B[i].x = fmaf(b.x, -w.y, B[i].x);
+                B[i].y = fmaf(b.y, -w.y, B[i].y);
+            }
+        }
+        float2* dst = out + seq * ss;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int r = g * G + i;
+            if (r <= h) {
+                dst[(size_t)(j * R + r) * es] = make_float2(A[i].x - SGN * B[i].y, A[i].y + SGN * B[i].x);
+                if (r > 0) dst[(size_t)(j * R + R - r) * es] = make_float2(A[i].x + SGN * B[i].y, A[i].y - SGN * B[i].x);
+            }
+        }
+    };
+    if (COLS) {
+        const int total = (NR * ngrp) << lg;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) one(idx & (nseq - 1), idx >> lg);
+    } else {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        for (int seq = warp; seq < nseq; seq += nwarps)
+            for (int o = lane; o < NR * ngrp; o += 32) one(seq, o);
+    }
+}
+
 // Full FFT of nseq sequences; ping-pongs between a and b, returns the buffer holding the result.
 // Must be called by all threads of the block; ends with a __syncthreads().
 template <int SGN, bool COLS>
@@ -297,7 +357,10 @@ __device__ float2* fft_smem(const FftPlanDev& P, float2* a, float2* b, int nseq,
             case 13: stockham_pass<13, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
             case 17: stockham_pass<17, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
             case 19: stockham_pass<19, SGN, COLS>(a, b, P, Ns, nseq, ss, es, lg); break;
-            default: stockham_pass_generic<SGN, COLS>(a, b, P, R, Ns, nseq, ss, es, lg); break;
+            default:
+                if (Ns == 1) stockham_pass_prime_first<SGN, COLS, 5>(a, b, P, R, nseq, ss, es, lg);
+                else stockham_pass_generic<SGN, COLS>(a, b, P, R, Ns, nseq, ss, es, lg);
+                break;
         }
         __syncthreads();
         Ns *= R;

@@ -105,6 +105,39 @@ def case_rfft2_irfft2(dev, h, w, planes=3):
     compare("irfft2(rfft2) %dx%d" % (h, w), y, x.float().double(), rel_l2=2e-6, max_rel=5e-6)
 
 
+def case_fcaffn_fft_stage(dev, h, w, b=1, c=2, big_phase=False):
+    """FCAFFN spectral stage (FDN_arch.py:410-418): irfft2(rd(rfft2(x)) * conv1_xa(amp) * exp(-i conv1_xp(pha))) through the three
+    FFT kernels (rows R2C, columns forward + modulation + inverse, rows C2R) against torch float64."""
+    wf = w // 2 + 1
+    x = rnd(b, c, h, w, seed=h + w)
+    x[:, 0] += 2.0
+    amp = rnd(b, 3, h, wf, seed=5).abs() * 3
+    pha = rnd(b, 3, h, wf, seed=6) * 3.14
+    wxa = rnd(c, 3, seed=7)
+    wxp = rnd(c, 3, seed=8)
+    if big_phase:                                   # phases beyond the fast sincos range take the library path
+        pha[:, :, 1::7, 2::5] *= 1.0e5
+    xd, ad, pd_ = dev32(x, dev), dev32(amp, dev), dev32(pha, dev)
+    spec = torch.empty(b, c, h, wf, 2, device=dev)
+    ops.fft_rows_r2c(xd, spec)
+    ops.fft_cols(spec, h * wf, wf, spec, h * wf, wf, b * c, h, wf, w, ops.COLS_FWD_MOD_INV, c, ad, pd_,
+                 dev32(wxa, dev).reshape(-1), dev32(wxp, dev).reshape(-1))
+    y = torch.empty(b, c, h, w, device=dev)
+    ops.fft_rows_c2r(spec, y, 1.0 / (h * w))
+    sync(dev)
+    x32 = x.float().double()
+    X = torch.fft.rfft2(x32)
+    re, im = X.real.clone(), X.imag.clone()
+    re[re.abs() < 1e-10] = 1e-10
+    im[im.abs() < 1e-10] = 1e-10
+    A = torch.einsum("cj,bjhw->bchw", wxa.float().double(), amp.float().double())
+    Pm = torch.einsum("cj,bjhw->bchw", wxp.float().double(), pha.float().double())
+    if big_phase:                                   # the kernel forms the phase in fp32: compare at the fp32-rounded phase
+        Pm = torch.einsum("cj,bjhw->bchw", wxp.float(), pha.float()).double()
+    ref = torch.fft.irfft2(torch.complex(re, im) * A * torch.exp(-1j * Pm), s=(h, w))
+    compare("fcaffn fft stage %dx%d" % (h, w), y, ref, rel_l2=3e-6 if not big_phase else 2e-3, max_rel=1e-5 if not big_phase else 1e-2)
+
+
 def case_irfft2_nonhermitian(dev, h, w):
     """irfft2 of an arbitrary (non-Hermitian) half spectrum, as produced by the modulated spectra."""
     planes = 2

@@ -31,6 +31,18 @@ def test_emu_fft(emu, h, w):
     P.case_irfft2_nonhermitian(emu, h, w)
 
 
+@pytest.mark.parametrize("h,w", [(16, 24), (64, 64), (46, 58)])
+def test_emu_fcaffn_fft_stage(emu, h, w):
+    P.case_fcaffn_fft_stage(emu, h, w)
+    P.case_fcaffn_fft_stage(emu, h, w, big_phase=True)
+
+
+def test_emu_fft_fast_and_prime_first(emu):
+    P.case_rfft2_irfft2(emu, 64, 64, planes=1)        # register-pipeline kernels (fft_fast.cuh)
+    P.case_rfft2_irfft2(emu, 46, 94, planes=1)        # 46 = 2*23, 47: prime radices first, no input twiddles
+    P.case_rfft2_irfft2(emu, 58, 1334, planes=1)      # 667 = 23*29: first-pass and general prime passes in one transform
+
+
 def test_emu_pointwise_and_convs(emu):
     P.case_pw_conv(emu)
     P.case_conv2d(emu)

@@ -30,6 +30,14 @@ def test_irfft2_nonhermitian(cuda_dev):
     P.case_irfft2_nonhermitian(cuda_dev, 160, 280)
 
 
+@pytest.mark.parametrize("h,w", [(640, 1120), (320, 560), (160, 280), (256, 256), (64, 64), (416, 608), (104, 152), (16, 24)])
+def test_fcaffn_fft_stage(cuda_dev, h, w):
+    """rows R2C -> columns forward + FCAFFN modulation + inverse -> rows C2R at every level of the BASELINE configs, vs torch float64;
+    also with phases beyond the fast sincos range (library path of the column kernel)."""
+    P.case_fcaffn_fft_stage(cuda_dev, h, w, b=2, c=3)
+    P.case_fcaffn_fft_stage(cuda_dev, h, w, b=1, c=2, big_phase=True)
+
+
 def test_pw_conv(cuda_dev):
     P.case_pw_conv(cuda_dev)
 
