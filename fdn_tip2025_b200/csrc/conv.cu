@@ -437,7 +437,19 @@ __device__ __forceinline__ void dw_row8(const float (&r0)[10], const float (&r1)
     }
 }
 
-// (Packed fp32x2 rows - FFMA2 / FMUL2, two outputs per issue slot, bit-identical - were measured neutral: the register moves that
+// the same row for a PAIR of output channels that read the same input rows: k[j] = (weight of output 0, weight of output 1)
+__device__ __forceinline__ void dw_row8_pair(const float (&r0)[10], const float (&r1)[10], const float (&r2)[10], const float2 (&k)[9], float2 (&o)[8]) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        float2 a = f2mul_s(k[0], r0[x]);
+        a = cfma(k[1], r0[x + 1], a); a = cfma(k[2], r0[x + 2], a);
+        a = cfma(k[3], r1[x], a); a = cfma(k[4], r1[x + 1], a); a = cfma(k[5], r1[x + 2], a);
+        a = cfma(k[6], r2[x], a); a = cfma(k[7], r2[x + 1], a); a = cfma(k[8], r2[x + 2], a);
+        o[x] = a;
+    }
+}
+
+// (Packed fp32x2 rows pairing along x - FFMA2 / FMUL2, two outputs per issue slot, bit-identical - were measured neutral: the register moves that
 // build the odd-aligned operand pairs eat the saved issue slots; 62.6 vs 60.9 ms per 8-image step.  Kept out.)
 #define DW_ROW8 dw_row8
 
@@ -479,7 +491,10 @@ __global__ void __launch_bounds__(128, MINB) k_dwconv3_w8(const float* __restric
         DW_ROW8(a0, a1, a2, ka, o);
         if (MODE >= 1) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) o[x] = fdn_gelu(o[x]);
+            for (int x = 0; x < 8; x += 2) {                        // two pixels per packed operation
+                const float2 t = fdn_gelu2(make_float2(o[x], o[x + 1]));
+                o[x] = t.x; o[x + 1] = t.y;
+            }
         }
         if (MODE == 2) {
             float o2[8];
@@ -520,13 +535,15 @@ __global__ void __launch_bounds__(128, MINB) k_dwgate_pair(const float* __restri
     const float* pa = in + ((size_t)b * C + m) * H * W;
     const float* pb = in + ((size_t)b * C + cb0) * H * W;
     const float* pd = in + ((size_t)b * C + cb1) * H * W;
-    float ka0[9], ka1[9], kb0[9], kb1[9];
+    // The two outputs of the pair share their input rows, so every tap is ONE packed FFMA2: (acc_2m, acc_2m+1) += (k_2m, k_2m+1) * in,
+    // the input a broadcast scalar operand and the weight / accumulator pairs in aligned register pairs - half the FMA issue slots of
+    // this issue-bound kernel with no operand shuffling (pairing along x instead needs odd-aligned pairs and was measured neutral).
+    // Same operation order as dw_row8 / fdn_gelu: bit-identical results.
+    float2 ka[9], kb[9];                      // (output 2m, output 2m+1) weights of the GELU branch / the linear branch
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-        ka0[j] = w[c0 * 9 + j];
-        kb0[j] = w[(C + c0) * 9 + j];
-        ka1[j] = has1 ? w[c1 * 9 + j] : 0.f;
-        kb1[j] = has1 ? w[(C + c1) * 9 + j] : 0.f;
+        ka[j] = make_float2(w[c0 * 9 + j], has1 ? w[c1 * 9 + j] : 0.f);
+        kb[j] = make_float2(w[(C + c0) * 9 + j], has1 ? w[(C + c1) * 9 + j] : 0.f);
     }
     float a0[10], a1[10], a2[10], b0[10], b1[10], b2[10], d0[ODD ? 10 : 1], d1[ODD ? 10 : 1], d2[ODD ? 10 : 1];
     dw_row10(pa, H, W, y0 - 1, x0, a0);
@@ -541,33 +558,34 @@ __global__ void __launch_bounds__(128, MINB) k_dwgate_pair(const float* __restri
     float* op1 = out + (((size_t)b * C + c1) * H + y0) * W + x0;
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
-        float g0[8], g1[8], l0[8], l1[8];
+        float2 g[8], l[8];
         dw_row10(pa, H, W, y0 + y + 1, x0, a2);
         dw_row10(pb, H, W, y0 + y + 1, x0, b2);
-        DW_ROW8(a0, a1, a2, ka0, g0);
-        DW_ROW8(a0, a1, a2, ka1, g1);
-        DW_ROW8(b0, b1, b2, kb0, l0);
+        dw_row8_pair(a0, a1, a2, ka, g);
         if (ODD) {
             dw_row10(pd, H, W, y0 + y + 1, x0, reinterpret_cast<float(&)[10]>(d2));
-            DW_ROW8(reinterpret_cast<float(&)[10]>(d0), reinterpret_cast<float(&)[10]>(d1), reinterpret_cast<float(&)[10]>(d2), kb1, l1);
+            float kx[9], ky[9], lx[8], ly[8];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { kx[j] = kb[j].x; ky[j] = kb[j].y; }
+            dw_row8(b0, b1, b2, kx, lx);
+            dw_row8(reinterpret_cast<float(&)[10]>(d0), reinterpret_cast<float(&)[10]>(d1), reinterpret_cast<float(&)[10]>(d2), ky, ly);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) l[x] = make_float2(lx[x], ly[x]);
 #pragma unroll
             for (int j = 0; j < 10; ++j) { d0[ODD ? j : 0] = d1[ODD ? j : 0]; d1[ODD ? j : 0] = d2[ODD ? j : 0]; }
         } else {
-            DW_ROW8(b0, b1, b2, kb1, l1);
+            dw_row8_pair(b0, b1, b2, kb, l);
         }
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            g0[x] = fdn_gelu(g0[x]) * l0[x];
-            g1[x] = fdn_gelu(g1[x]) * l1[x];
-        }
+        for (int x = 0; x < 8; ++x) g[x] = fdn_gelu_gate2(g[x], l[x]);
 #pragma unroll
         for (int j = 0; j < 10; ++j) { a0[j] = a1[j]; a1[j] = a2[j]; b0[j] = b1[j]; b1[j] = b2[j]; }
         if (y0 + y < H) {
-            *reinterpret_cast<float4*>(op0 + (size_t)y * W) = make_float4(g0[0], g0[1], g0[2], g0[3]);
-            *reinterpret_cast<float4*>(op0 + (size_t)y * W + 4) = make_float4(g0[4], g0[5], g0[6], g0[7]);
+            *reinterpret_cast<float4*>(op0 + (size_t)y * W) = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+            *reinterpret_cast<float4*>(op0 + (size_t)y * W + 4) = make_float4(g[4].x, g[5].x, g[6].x, g[7].x);
             if (has1) {
-                *reinterpret_cast<float4*>(op1 + (size_t)y * W) = make_float4(g1[0], g1[1], g1[2], g1[3]);
-                *reinterpret_cast<float4*>(op1 + (size_t)y * W + 4) = make_float4(g1[4], g1[5], g1[6], g1[7]);
+                *reinterpret_cast<float4*>(op1 + (size_t)y * W) = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
+                *reinterpret_cast<float4*>(op1 + (size_t)y * W + 4) = make_float4(g[4].y, g[5].y, g[6].y, g[7].y);
             }
         }
     }

@@ -52,8 +52,22 @@ static inline int fdn_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 // ---- small device helpers --------------------------------------------------------------------------
 #ifdef FDN_EMU
 #define FDN_EXPF(x) expf(x)
+__device__ __forceinline__ float fdn_rcp_fast(float x) { return 1.0f / x; }
 #else
-#define FDN_EXPF(x) __expf(x)
+// e^x = ex2.approx.ftz(x log2 e) and 1/x = rcp.approx.ftz(x) as single MUFU operations: __expf / __fdividef wrap the same
+// instructions in denormal-range scaling (a compare and two multiplies each) that the GELU arguments never need - a result below
+// 2^-126 is flushed to zero, where it multiplies into an output of that size anyway.
+__device__ __forceinline__ float fdn_exp_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float fdn_rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#define FDN_EXPF(x) fdn_exp_fast(x)
 #endif
 // erf-form GELU (F.gelu default): 0.5 x (1 + erf(x / sqrt 2)), evaluated through erfc(z) = t P(t) e^{-z^2}, t = 1/(1 + 0.39 z), z = |x| / sqrt 2
 // (degree-6 fit, |error| < 2e-8 before rounding).  Writing 1 + erf as 2 - erfc / erfc keeps small results of negative arguments
@@ -61,7 +75,7 @@ static inline int fdn_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 // at about half the instructions: two MUFU (rcp, ex2) and ten FMA-pipe operations.
 __device__ __forceinline__ float fdn_gelu(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.39f, z, 1.0f));
+    const float t = fdn_rcp_fast(fmaf(0.39f, z, 1.0f));
     float q = fmaf(-2.280578155e-01f, t, 8.887884326e-01f);
     q = fmaf(q, t, -6.388445279e-01f);
     q = fmaf(q, t, 6.523336912e-01f);
@@ -69,6 +83,71 @@ __device__ __forceinline__ float fdn_gelu(float x) {
     q = fmaf(q, t, 2.355015248e-01f);
     const float ec = q * t * FDN_EXPF(-z * z);              // erfc(z)
     return 0.5f * x * (x >= 0.f ? 2.0f - ec : ec);
+}
+// ---- packed fp32x2 helpers (Blackwell FMUL2 / FFMA2; scalar forms in the emulation build, bit-identical) ----------------------------
+// A scalar operand written as the pair {s, s} is encoded by ptxas as a broadcast register operand (no move).
+#ifdef FDN_EMU
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 f2mul_s(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 f2fma_c(float2 a, float2 b, float c) { return make_float2(fmaf(a.x, b.x, c), fmaf(a.y, b.y, c)); }
+#else
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2mul_s(float2 a, float s) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2fma_c(float2 a, float2 b, float c) {   // a*b + {c, c}
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %6}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c));
+    return r;
+}
+#endif
+// gelu of two values at once (and gelu(g) * l below): the same operation sequence as fdn_gelu (bit-identical), the polynomial and the
+// products packed
+__device__ __forceinline__ float2 fdn_gelu2(float2 g) {
+    const float2 z = make_float2(fabsf(g.x) * 0.70710678118654752440f, fabsf(g.y) * 0.70710678118654752440f);
+    const float2 den = f2fma_c(make_float2(0.39f, 0.39f), z, 1.0f);
+    const float2 t = make_float2(fdn_rcp_fast(den.x), fdn_rcp_fast(den.y));
+    float2 q = f2fma_c(make_float2(-2.280578155e-01f, -2.280578155e-01f), t, 8.887884326e-01f);
+    q = f2fma_c(q, t, -6.388445279e-01f);
+    q = f2fma_c(q, t, 6.523336912e-01f);
+    q = f2fma_c(q, t, 9.027867826e-02f);
+    q = f2fma_c(q, t, 2.355015248e-01f);
+    const float2 nz2 = f2mul(make_float2(-z.x, -z.y), z);
+    const float2 e = make_float2(FDN_EXPF(nz2.x), FDN_EXPF(nz2.y));
+    const float2 ec = f2mul(f2mul(q, t), e);
+    const float2 sel = make_float2(g.x >= 0.f ? 2.0f - ec.x : ec.x, g.y >= 0.f ? 2.0f - ec.y : ec.y);
+    return f2mul(f2mul_s(g, 0.5f), sel);
+}
+__device__ __forceinline__ float2 fdn_gelu_gate2(float2 g, float2 l) {
+    const float2 z = make_float2(fabsf(g.x) * 0.70710678118654752440f, fabsf(g.y) * 0.70710678118654752440f);
+    const float2 den = f2fma_c(make_float2(0.39f, 0.39f), z, 1.0f);
+    const float2 t = make_float2(fdn_rcp_fast(den.x), fdn_rcp_fast(den.y));
+    float2 q = f2fma_c(make_float2(-2.280578155e-01f, -2.280578155e-01f), t, 8.887884326e-01f);
+    q = f2fma_c(q, t, -6.388445279e-01f);
+    q = f2fma_c(q, t, 6.523336912e-01f);
+    q = f2fma_c(q, t, 9.027867826e-02f);
+    q = f2fma_c(q, t, 2.355015248e-01f);
+    const float2 nz2 = f2mul(make_float2(-z.x, -z.y), z);
+    const float2 e = make_float2(FDN_EXPF(nz2.x), FDN_EXPF(nz2.y));
+    const float2 ec = f2mul(f2mul(q, t), e);
+    const float2 sel = make_float2(g.x >= 0.f ? 2.0f - ec.x : ec.x, g.y >= 0.f ? 2.0f - ec.y : ec.y);
+    return f2mul(f2mul(f2mul_s(g, 0.5f), sel), l);
 }
 __device__ __forceinline__ float fdn_lrelu(float x) { return x > 0.f ? x : 0.1f * x; }
 __device__ __forceinline__ float fdn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
