@@ -205,12 +205,11 @@ FDN_API int fdn_conv2d(const float* in, const float* w, const float* bias, const
 #define FILM_CG 8
 __global__ void __launch_bounds__(256) k_film_maps(const float* __restrict__ img, const float* __restrict__ wmul, const float* __restrict__ wadd,
                                                    float* __restrict__ omul, float* __restrict__ oadd, int C, int H, int W) {
-    __shared__ __align__(16) float sw[2][FILM_CG][28];       // 27 taps (+1 pad) per channel and map
+    __shared__ __align__(16) float2 sw[FILM_CG][28];         // 27 taps (+1 pad) per channel: (mul weight, add weight)
     const int c0 = blockIdx.y * FILM_CG, b = blockIdx.z;
-    for (int i = threadIdx.x; i < 2 * FILM_CG * 27; i += blockDim.x) {
-        const int m = i / (FILM_CG * 27), r = i - m * FILM_CG * 27, c = r / 27, t = r - c * 27;
-        const float* src = m == 0 ? wmul : wadd;
-        sw[m][c][t] = (c0 + c < C) ? src[(c0 + c) * 27 + t] : 0.f;
+    for (int i = threadIdx.x; i < FILM_CG * 27; i += blockDim.x) {
+        const int c = i / 27, t = i - c * 27;
+        sw[c][t] = (c0 + c < C) ? make_float2(wmul[(c0 + c) * 27 + t], wadd[(c0 + c) * 27 + t]) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     const int W4 = W >> 2;
@@ -234,23 +233,23 @@ __global__ void __launch_bounds__(256) k_film_maps(const float* __restrict__ img
                 for (int dx = 0; dx < 6; ++dx) nb[j][dy][dx] = 0.f;
             }
         }
+    // the two maps of a channel read the same 27 inputs: one packed FFMA2 per tap and pixel, (mul, add) += (w_mul, w_add) * input,
+    // and one 64-bit weight read per tap instead of two
     for (int c = 0; c < FILM_CG && c0 + c < C; ++c) {
+        float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float2 wv = sw[c][(j * 3 + dy) * 3 + dx];
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const float wv = sw[m][c][(j * 3 + dy) * 3 + dx];
-#pragma unroll
-                        for (int px = 0; px < 4; ++px) o[px] += wv * nb[j][dy][px + dx];
-                    }
-            float* dst = (m == 0 ? omul : oadd) + (((size_t)b * C + c0 + c) * H + y) * W + x0;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        }
+                    for (int px = 0; px < 4; ++px) o[px] = cfma(wv, nb[j][dy][px + dx], o[px]);
+                }
+        const size_t at = (((size_t)b * C + c0 + c) * H + y) * W + x0;
+        *reinterpret_cast<float4*>(omul + at) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        *reinterpret_cast<float4*>(oadd + at) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
     }
 }
 

@@ -91,7 +91,14 @@ __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2
 __device__ __forceinline__ float2 f2mul_s(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 __device__ __forceinline__ float2 f2fma_c(float2 a, float2 b, float c) { return make_float2(fmaf(a.x, b.x, c), fmaf(a.y, b.y, c)); }
+__device__ __forceinline__ float2 f2add_s(float2 a, float s) { return make_float2(a.x + s, a.y + s); }
 #else
+__device__ __forceinline__ float2 f2add_s(float2 a, float s) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
     float2 r;
     asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"

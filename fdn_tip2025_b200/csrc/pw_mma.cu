@@ -566,28 +566,34 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                                 g4 = *reinterpret_cast<const float4*>(gam_kb + 4 * c);
                                 b4 = *reinterpret_cast<const float4*>(bet_kb + 4 * c);
                             }
-                            const float gj[4] = {g4.x, g4.y, g4.z, g4.w}, bj[4] = {b4.x, b4.y, b4.z, b4.w};
+                            // two channels per packed operation (FADD2 / FMUL2 / FFMA2 with the per-pixel statistics as broadcast
+                            // operands): same operation order as the scalar form, so the operand bits are unchanged
+                            const float2 gp[2] = {make_float2(g4.x, g4.y), make_float2(g4.z, g4.w)};
+                            const float2 bp[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int kk = 4 * c + j;
-                                float x = raw[kk * MMA_TP];
+                            for (int jp = 0; jp < 2; ++jp) {
+                                const int kk = 4 * c + 2 * jp;
+                                float2 x = make_float2(raw[kk * MMA_TP], raw[(kk + 1) * MMA_TP]);
                                 if (PRO == 1) {
-                                    x = (x - mu) * rs * gj[j] + bj[j];
+                                    x = f2fma(f2mul_s(f2add_s(x, -mu), rs), gp[jp], bp[jp]);
                                 } else if (PRO == 2) {
-                                    // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el
+                                    // grouped layout: kk = g*10 + el, channel g*E + kb*10 + el, v_value row el (kk even: a pair never straddles groups)
                                     const int g = kk / MMA_EB, el = kk - g * MMA_EB;
                                     if (g < 3) {
                                         const float gm = g == 0 ? gmu0 : (g == 1 ? gmu1 : gmu2), gr = g == 0 ? grs0 : (g == 1 ? grs1 : grs2);
-                                        x = ((x - gm) * gr * gj[j] + bj[j]) * raw[MMA_P2_V_OFF / 4 + el * MMA_TP];
+                                        const float2 vv = make_float2(raw[MMA_P2_V_OFF / 4 + el * MMA_TP], raw[MMA_P2_V_OFF / 4 + (el + 1) * MMA_TP]);
+                                        x = f2mul(f2fma(f2mul_s(f2add_s(x, -gm), gr), gp[jp], bp[jp]), vv);
                                     } else {
-                                        x = 0.f;          // rows 30, 31 of a grouped block
+                                        x = make_float2(0.f, 0.f);          // rows 30, 31 of a grouped block
                                     }
                                 } else if (PRO == 3) {
-                                    const float x1 = raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP];
-                                    x = ((x - mu) * rs * gj[j] + bj[j]) * x1 + x1;
+                                    const float2 x1 = make_float2(raw[(MMA_SLOT_BYTES / 4) + kk * MMA_TP], raw[(MMA_SLOT_BYTES / 4) + (kk + 1) * MMA_TP]);
+                                    x = f2fma(f2fma(f2mul_s(f2add_s(x, -mu), rs), gp[jp], bp[jp]), x1, x1);
                                 }
-                                hi[j] = to_tf32(x);
-                                lo[j] = x - hi[j];      // exact; the tensor core reads only the tf32 bits of it (truncation: 2^-21 |x|, the size of the dropped lo*lo term)
+                                const float2 h = make_float2(to_tf32(x.x), to_tf32(x.y));
+                                const float2 l = csub(x, h);      // exact; the tensor core reads only the tf32 bits of it (truncation: 2^-21 |x|, the size of the dropped lo*lo term)
+                                hi[2 * jp] = h.x; hi[2 * jp + 1] = h.y;
+                                lo[2 * jp] = l.x; lo[2 * jp + 1] = l.y;
                             }
                             *reinterpret_cast<float4*>(stage + soff[i]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                             if (PASSES == 3) *reinterpret_cast<float4*>(stage + a_bytes + soff[i]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
