@@ -39,22 +39,6 @@ struct PwParams {
 #define PW_TP 128
 #define PW_KC 32
 
-__device__ __forceinline__ float pw_load(const PwParams& q, int b, int k, int p) {
-    int s = 0;
-    while (s + 1 < q.nsrc && k >= q.src[s].C) { k -= q.src[s].C; ++s; }
-    const PwSrc& S = q.src[s];
-    size_t idx;
-    if (S.shift == 0) {
-        idx = ((size_t)b * S.C + k) * ((size_t)q.H * q.W) + p;
-    } else {
-        int y = p / q.W, x = p - y * q.W;
-        int ys = S.shift > 0 ? (y >> S.shift) : (y << -S.shift);
-        int xs = S.shift > 0 ? (x >> S.shift) : (x << -S.shift);
-        idx = (((size_t)b * S.C + k) * S.Hs + ys) * S.Ws + xs;
-    }
-    return S.p[idx];
-}
-
 template <int NPT>
 __global__ void __launch_bounds__(256) k_pw_conv(PwParams q) {
     constexpr int TN = 8 * NPT;
@@ -94,17 +78,49 @@ __global__ void __launch_bounds__(256) k_pw_conv(PwParams q) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    // Staging: a thread always stages the same pixel (256 threads = 2 channels x 128 pixels), so the pixel's offset inside every source
+    // - including the nearest-resampled ones of the torch.cat-fused convolutions - is computed once, not per element (a run-time
+    // division and a source search per element made the 84-channel fourier_fuse convolution 3 ms per launch).
+    const int spp = tid & (PW_TP - 1), skk0 = tid >> 7;
+    const int sp = p0 + spp;
+    const bool sp_ok = sp < HW;
+    const float* sbase[3] = {nullptr, nullptr, nullptr};
+    size_t sstride[3] = {0, 0, 0};
+    int send[3] = {0, 0, 0}, sbeg[3] = {0, 0, 0};                  // channel range [sbeg, send) of source s
+    {
+        const int y = sp_ok ? sp / q.W : 0, x = sp_ok ? sp - y * q.W : 0;
+        int cum = 0;
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            if (s < q.nsrc) {
+                const PwSrc& S = q.src[s];
+                size_t off;
+                if (S.shift == 0) {
+                    sstride[s] = (size_t)HW;
+                    off = (size_t)(sp_ok ? sp : 0);
+                } else {
+                    const int ys = S.shift > 0 ? (y >> S.shift) : (y << -S.shift);
+                    const int xs = S.shift > 0 ? (x >> S.shift) : (x << -S.shift);
+                    sstride[s] = (size_t)S.Hs * S.Ws;
+                    off = (size_t)ys * S.Ws + xs;
+                }
+                sbase[s] = S.p + (size_t)b * S.C * sstride[s] + off;
+                sbeg[s] = cum;
+                cum += S.C;
+                send[s] = cum;
+            }
+    }
     for (int k0 = 0; k0 < q.K; k0 += PW_KC) {
 #pragma unroll 4
-        for (int i = tid; i < PW_KC * PW_TP; i += 256) {
-            int kk = i / PW_TP, pp = i - kk * PW_TP;
-            int k = k0 + kk, p = p0 + pp;
+        for (int kk = skk0; kk < PW_KC; kk += 2) {
+            const int k = k0 + kk;
             float v = 0.f;
-            if (k < q.K && p < HW) {
-                v = pw_load(q, b, k, p);
-                if (ln) v = (v - s_mu[pp]) * s_rs[pp] * q.ln_w[k] + q.ln_b[k];
+            if (k < q.K && sp_ok) {
+                const int s = (k < send[0] || q.nsrc == 1) ? 0 : ((k < send[1] || q.nsrc == 2) ? 1 : 2);
+                v = sbase[s][(size_t)(k - sbeg[s]) * sstride[s]];
+                if (ln) v = (v - s_mu[spp]) * s_rs[spp] * q.ln_w[k] + q.ln_b[k];
             }
-            Xs[kk][pp] = v;
+            Xs[kk][spp] = v;
         }
         for (int i = tid; i < PW_KC * TN; i += 256) {
             int kk = i / TN, nn = i - kk * TN;
@@ -135,6 +151,13 @@ __global__ void __launch_bounds__(256) k_pw_conv(PwParams q) {
     const float scale = q.img_scale ? q.img_scale[b] : 1.0f;
     const bool flat = (q.out_rs == q.W) && (q.out_ps == (long long)HW) && ((HW & 3) == 0);
     const int pbase = p0 + 4 * tx;
+    size_t ooff[4];                                                 // strided output view: row / column of the four pixels, once
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = pbase + j < HW ? pbase + j : 0;
+        const int y = p / q.W, x = p - y * q.W;
+        ooff[j] = (size_t)y * q.out_rs + x;
+    }
 #pragma unroll
     for (int i = 0; i < NPT; ++i) {
         int n = n0 + ty * NPT + i;
@@ -158,10 +181,7 @@ __global__ void __launch_bounds__(256) k_pw_conv(PwParams q) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int p = pbase + j;
-                if (p < HW) {
-                    int y = p / q.W, x = p - y * q.W;
-                    q.out[(size_t)b * q.out_bs + (size_t)n * q.out_ps + (size_t)y * q.out_rs + x] = v[j];
-                }
+                if (p < HW) q.out[(size_t)b * q.out_bs + (size_t)n * q.out_ps + ooff[j]] = v[j];
             }
         }
     }
@@ -299,6 +319,44 @@ __global__ void k_up2_bilinear(const float* __restrict__ in, float* __restrict__
     out[i] = (1.f - ly) * top + ly * bot;
 }
 
+// four horizontally adjacent outputs per thread (W even): the same taps and the same arithmetic per output as k_up2_bilinear, with the
+// row / plane decomposition, the two source rows and the 128-bit store shared by the four (the scalar kernel ran at 1 TB/s on index
+// arithmetic: three run-time divisions and four scattered loads per output)
+__global__ void __launch_bounds__(256) k_up2_bilinear4(const float* __restrict__ in, float* __restrict__ out, int H, int W, long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over planes*2H*(2W/4)
+    if (i >= total4) return;
+    const int Wo = 2 * W, Ho = 2 * H, Wq = Wo >> 2;
+    const int xq = (int)(i % Wq);
+    long long t = i / Wq;
+    const int y = (int)(t % Ho);
+    const long long pl = t / Ho;
+    const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0;
+    const float* r0 = in + ((size_t)pl * H + y0) * W;
+    const float* r1 = in + ((size_t)pl * H + y1) * W;
+    // outputs 4 xq .. 4 xq + 3 read source columns 2 xq - 1 .. 2 xq + 2 (clamped)
+    const int c = 2 * xq;
+    const int cm = max(c - 1, 0), cp = min(c + 2, W - 1);
+    const float a0 = r0[cm], a1 = r0[c], a2 = r0[c + 1], a3 = r0[cp];
+    const float b0 = r1[cm], b1 = r1[c], b2 = r1[c + 1], b3 = r1[cp];
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = 4 * xq + j;
+        const float sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+        const int x0 = (int)sx;
+        const float lx = sx - x0;
+        // (x0, x1) is (cm, c), (c, c + 1), (c, c + 1), (c + 1, cp) for j = 0..3; at the left border x0 = x1 = 0 = cm = c
+        const float t0 = j == 0 ? a0 : (j == 3 ? a2 : a1), t1 = j == 0 ? a1 : (j == 3 ? a3 : a2);
+        const float u0 = j == 0 ? b0 : (j == 3 ? b2 : b1), u1 = j == 0 ? b1 : (j == 3 ? b3 : b2);
+        const float top = (1.f - lx) * t0 + lx * t1;
+        const float bot = (1.f - lx) * u0 + lx * u1;
+        o[j] = (1.f - ly) * top + ly * bot;
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)pl * Ho + y) * Wo + 4 * xq) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 __global__ void k_pixel_unshuffle(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W, int r, long long total) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*C*r*r*(H/r)*(W/r)
     if (i >= total) return;
@@ -344,6 +402,10 @@ FDN_API int fdn_avgpool2(const float* in, float* out, int planes, int H, int W, 
 FDN_API int fdn_up2_bilinear(const float* in, float* out, int planes, int H, int W, cudaStream_t st) {
     FDN_REQUIRE(in && out && planes > 0 && H > 0 && W > 0, "bad arguments");
     long long n = (long long)planes * H * W * 4;
+    if (W % 2 == 0 && W >= 2 && fdn_aligned16(out)) {
+        FDN_LAUNCH_SEQ(k_up2_bilinear4, dim3(fdn_cdiv(n / 4, 256)), dim3(256), 0, st, in, out, H, W, n / 4);
+        return fdn_check_launch("k_up2_bilinear4");
+    }
     FDN_LAUNCH_SEQ(k_up2_bilinear, dim3(fdn_cdiv(n, 256)), dim3(256), 0, st, in, out, H, W, n);
     return fdn_check_launch("k_up2_bilinear");
 }
