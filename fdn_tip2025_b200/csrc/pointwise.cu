@@ -187,6 +187,99 @@ __global__ void __launch_bounds__(256) k_pw_conv(PwParams q) {
     }
 }
 
+// Few output channels (N <= NO <= 16; the level-1 convolutions of MAR: 84 -> 12, 12 -> 12, 12 -> 3): a thread owns four adjacent pixels and
+// ALL outputs.  Inputs come straight from global memory (one 128-bit load per channel, or four cached scalar loads for a
+// nearest-resampled source), the weights of a channel are NO / 4 broadcast 128-bit shared-memory reads feeding 4 NO FMAs - no input
+// staging, no barrier in the K loop, no output tile padded to 32 channels (k_pw_conv spent 3 ms on the 84 -> 12 fourier_fuse
+// convolution).  Same accumulation order over k as k_pw_conv.
+#define PWS_MAXK 256
+template <int NO>
+__global__ void __launch_bounds__(256) k_pw_conv_small(PwParams q) {
+    __shared__ __align__(16) float sw[PWS_MAXK * NO];
+    const int HW = q.H * q.W, b = blockIdx.z;
+    for (int i = threadIdx.x; i < q.K * NO; i += blockDim.x) {
+        const int k = i / NO, n = i - k * NO;
+        sw[i] = n < q.N ? q.wt[(size_t)k * q.N + n] : 0.f;
+    }
+    __syncthreads();
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4;             // HW % 4 == 0, W % 4 == 0: the four pixels share a row
+    if (p >= HW) return;
+    const int y = p / q.W, x = p - y * q.W;
+    float acc[4][NO];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int n = 0; n < NO; ++n) acc[j][n] = 0.f;
+    int kg = 0;
+    for (int s = 0; s < q.nsrc; ++s) {
+        const PwSrc& S = q.src[s];
+        const float* wrow = sw + kg * NO;
+        if (S.shift == 0) {
+            const float* xp = S.p + (size_t)b * S.C * HW + p;
+#pragma unroll 2
+            for (int k = 0; k < S.C; ++k) {
+                const float4 xv = *reinterpret_cast<const float4*>(xp + (size_t)k * HW);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int n4 = 0; n4 < NO; n4 += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k * NO + n4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][n4] += w4.x * xs[j]; acc[j][n4 + 1] += w4.y * xs[j];
+                        acc[j][n4 + 2] += w4.z * xs[j]; acc[j][n4 + 3] += w4.w * xs[j];
+                    }
+                }
+            }
+        } else {
+            const int ys = S.shift > 0 ? (y >> S.shift) : (y << -S.shift);
+            int xo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xo[j] = S.shift > 0 ? ((x + j) >> S.shift) : ((x + j) << -S.shift);
+            const size_t plane = (size_t)S.Hs * S.Ws;
+            const float* xp = S.p + (size_t)b * S.C * plane + (size_t)ys * S.Ws;
+#pragma unroll 2
+            for (int k = 0; k < S.C; ++k) {
+                const float* r = xp + (size_t)k * plane;
+                const float xs[4] = {r[xo[0]], r[xo[1]], r[xo[2]], r[xo[3]]};
+#pragma unroll
+                for (int n4 = 0; n4 < NO; n4 += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k * NO + n4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][n4] += w4.x * xs[j]; acc[j][n4 + 1] += w4.y * xs[j];
+                        acc[j][n4 + 2] += w4.z * xs[j]; acc[j][n4 + 3] += w4.w * xs[j];
+                    }
+                }
+            }
+        }
+        kg += S.C;
+    }
+    const float scale = q.img_scale ? q.img_scale[b] : 1.0f;
+    const bool flat = (q.out_rs == q.W) && (q.out_ps == (long long)HW);
+    const size_t ooff = (size_t)y * q.out_rs + x;
+#pragma unroll
+    for (int n = 0; n < NO; ++n) {
+        if (n >= q.N) break;
+        const float bias = q.bias ? q.bias[n] : 0.f;
+        const size_t cidx = ((size_t)b * q.N + n) * HW + p;              // compact [B][N][H][W] index of film / res
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = fdn_act(acc[j][n] + bias, q.act);
+            if (q.film_mul) t = t * q.film_mul[cidx + j] + q.film_add[cidx + j];
+            if (q.res) t += q.res_coef * q.res[cidx + j];
+            v[j] = t * scale;
+        }
+        float* o = q.out + (size_t)b * q.out_bs + (size_t)n * q.out_ps + ooff;
+        if (flat && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = v[j];
+        }
+    }
+}
+
 // Generic 1x1 convolution.  Sources are concatenated along channels; src_shift[i] > 0 means source i is 2^s times
 // smaller and is nearest-upsampled, < 0 means it is larger and is nearest-downsampled (x[::2^s, ::2^s]).
 // wt is the weight transposed to [K][N].  Epilogue order: +bias, act, *film_mul+film_add, +res_coef*res, *img_scale[b].
@@ -226,6 +319,14 @@ FDN_API int fdn_pw_conv(const float* src0, int c0, int shift0, const float* src1
     q.out = out; q.out_bs = out_bs; q.out_ps = out_ps; q.out_rs = out_rs;
     FDN_REQUIRE(fdn_aligned16(out) || !(out_rs == W && out_ps == (long long)H * W), "output must be 16-byte aligned");
     int HW = H * W;
+    if (N <= 16 && ln_w == nullptr && q.K <= PWS_MAXK && W % 4 == 0) {
+        dim3 grid(fdn_cdiv(HW / 4, 256), 1, B);
+        if (N <= 4) { auto k = k_pw_conv_small<4>; FDN_LAUNCH(k, grid, dim3(256), 0, st, q); }
+        else if (N <= 8) { auto k = k_pw_conv_small<8>; FDN_LAUNCH(k, grid, dim3(256), 0, st, q); }
+        else if (N <= 12) { auto k = k_pw_conv_small<12>; FDN_LAUNCH(k, grid, dim3(256), 0, st, q); }
+        else { auto k = k_pw_conv_small<16>; FDN_LAUNCH(k, grid, dim3(256), 0, st, q); }
+        return fdn_check_launch("k_pw_conv_small");
+    }
     if (N <= 32) {
         auto k = k_pw_conv<4>;
         FDN_LAUNCH(k, dim3(fdn_cdiv(HW, PW_TP), fdn_cdiv(N, 32), B), dim3(256), 0, st, q);

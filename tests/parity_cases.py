@@ -179,6 +179,24 @@ def case_pw_conv(dev):
     ln = (xf - mu) / torch.sqrt(var + 1e-5) * g.float().double().view(1, -1, 1, 1) + bt.float().double().view(1, -1, 1, 1)
     ref = F.conv2d(ln, wgt.float().double()[:, :, None, None]) * fm.float().double() + fa.float().double()
     compare("pw_conv ln/film", out, ref, rel_l2=2e-6, max_rel=5e-6)
+    # few-output-channel kernel (N <= 16): three resampled sources, bias, FiLM, residual, scale, written into a padded view (fourier_fuse)
+    for n in (12, 3, 16):
+        wgt, bias = rnd(n, 15, seed=20 + n), rnd(n, seed=21 + n)
+        fm, fa, res = rnd(b, n, h, w, seed=22), rnd(b, n, h, w, seed=23), rnd(b, n, h, w, seed=24)
+        hp, wp = h + 2, w + 2
+        pad = torch.zeros(b, n, hp, wp, device=dev)
+        ops.pw_conv([(dev32(s0, dev), 0), (dev32(s1, dev), 1), (dev32(s2, dev), -1)], dev32(wgt.t(), dev), pad.view(-1)[wp + 1:], bias=dev32(bias, dev),
+                    act=1, film=(dev32(fm, dev), dev32(fa, dev)), res=dev32(res, dev), res_coef=0.5, img_scale=dev32(scale, dev),
+                    out_view=(h, w, n * hp * wp, hp * wp, wp))
+        sync(dev)
+        ref = F.leaky_relu(F.conv2d(cat, wgt.float().double()[:, :, None, None], bias.float().double()), 0.1)
+        ref = ((ref * fm.float().double() + fa.float().double()) + 0.5 * res.float().double()) * scale.float().double().view(b, 1, 1, 1)
+        compare("pw_conv small N=%d (view)" % n, pad[:, :, 1:-1, 1:-1], ref, rel_l2=2e-6, max_rel=5e-6)
+        assert float(pad[:, :, 0].abs().max()) == 0 and float(pad[:, :, :, 0].abs().max()) == 0, "border of the padded view was written"
+        out = torch.empty(b, n, h, w, device=dev)
+        ops.pw_conv([(dev32(s0, dev), 0)], dev32(wgt[:, :5].t(), dev), out)
+        sync(dev)
+        compare("pw_conv small N=%d plain" % n, out, F.conv2d(s0.float().double(), wgt[:, :5].float().double()[:, :, None, None]), rel_l2=2e-6, max_rel=5e-6)
 
 
 def case_conv2d(dev):
