@@ -171,6 +171,7 @@ static int launch_conv_no(ConvParams& q, cudaStream_t st) {
 template <int K, int S>
 static int launch_conv(ConvParams& q, cudaStream_t st) {
     if (K == 3 && q.Cout >= 16 && q.Cout % 16 == 0) return launch_conv_no<K, S, 16>(q, st);
+    if (K == 3 && S == 1 && q.Cout <= 4) return launch_conv_no<K, S, 4>(q, st);      // RGB heads (32 -> 3, 12 -> 3): no 8-wide output tile to pad
     return launch_conv_no<K, S, 8>(q, st);
 }
 
