@@ -295,10 +295,10 @@ def _fdffn(cx, x, p):
     hid = _new(x, b, hd, h, w)
     _conv1x1(cx, [x], p + "ffn.project_in.weight", hid, ln=cx.ln(p + "norm2."))
     s1 = _new(x, b, hd, h, w)
-    if os.environ.get("FDN_B200_FDFFN_FUSED") == "1":
-        # dw3x3 -> GELU -> dw3x3 in shared-memory tiles + the 8x8 patch-FFT branch + their sum in one kernel.  Measured on
-        # B200 (r1): 84.6 ms vs 43 ms per 4 images for the three kernels below - the halo recompute of erf-GELU and the
-        # half-idle FFT phase make it compute-bound while the unfused kernels stream at ~3.5 TB/s - so it is opt-in.
+    if os.environ.get("FDN_B200_FDFFN_FUSED", "1") != "0":
+        # dw3x3 -> GELU -> dw3x3, the 8x8 patch-FFT branch and their sum in one kernel, one thread per (channel, patch) with rolling rows
+        # in registers: the Hd-channel s1 tensor never exists in HBM (one write + one read less per FDFFN).  Same-box A/B on B200:
+        # 348.8 vs 357.9 ms per 8-image step against the two kernels below (FDN_B200_FDFFN_FUSED=0).
         ops.fdffn_spatial(hid, cx.flat(p + "ffn.space.0.weight"), cx.flat(p + "ffn.space.2.weight"), cx.ffn_spec(p + "ffn."), s1)
         s2 = hid
     else:

@@ -225,6 +225,107 @@ __global__ void __launch_bounds__(128, 4) k_fdffn_patch_dw(const float* __restri
     store_patch(out + off, W, p);
 }
 
+// FDFFN middle section per patch, nothing through HBM (FDN_arch.py:457-470):
+//     out = irfft2_8x8(rd(rfft2_8x8(h)) * wspec) + dw_b(gelu(dw_a(h)))
+// One thread per (channel, patch).  The spectral branch is computed first into p[64].  The spatial branch then runs as a rolling
+// pipeline over the twelve input rows of the patch's halo-2 window: three rows of h (12 wide) give one row of s1 = gelu(dw_a(h)) on
+// the halo-1 window (10 wide, zero outside the image - it is dw_b's zero padding), and that row is scattered into the (up to) three
+// output rows it contributes to, so only one row of s1 is ever live.  Against the two-kernel form (GELU depthwise kernel writing s1,
+// k_fdffn_patch_dw reading it back with a halo) this removes a write and a read of the Hd-channel tensor per FDFFN at the price of
+// evaluating gelu(dw_a) on 100 instead of 64 positions per patch.
+__device__ __forceinline__ void load_row12(const float* __restrict__ plane, int H, int W, int yy, int x0, float r[12]) {
+    if (yy >= 0 && yy < H) {
+        const float* p = plane + (size_t)yy * W + x0;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        float2 l = make_float2(0.f, 0.f), rr = l;
+        if (x0 > 0) l = *reinterpret_cast<const float2*>(p - 2);              // x0 is a multiple of 8: 8-byte aligned
+        if (x0 + 8 < W) rr = *reinterpret_cast<const float2*>(p + 8);
+        r[0] = l.x; r[1] = l.y;
+        r[2] = a.x; r[3] = a.y; r[4] = a.z; r[5] = a.w; r[6] = b.x; r[7] = b.y; r[8] = b.z; r[9] = b.w;
+        r[10] = rr.x; r[11] = rr.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[i] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(128, 3) k_fdffn_patch_fused(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ wb,
+                                                              const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W,
+                                                              int per_plane) {
+    // grid.y = plane (b*C + c): channel, spectral weights and depthwise taps are uniform over the CTA
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;     // over (H/8)*(W/8)
+    if (item >= per_plane) return;
+    const int pw = W >> 3;
+    const int px = item % pw, py = item / pw;
+    const size_t plane = blockIdx.y;
+    const int c = blockIdx.y % C;
+    const int x0 = px * 8, y0 = py * 8;
+    const float* hp = h + plane * H * W;
+    const size_t off = plane * H * W + (size_t)y0 * W + x0;
+    float p[64];
+    {
+        float2 S[8][5];
+        load_patch(h + off, W, p);
+        rfft2_8x8(p, S);
+        const float2* w = wspec + c * 40;
+#pragma unroll
+        for (int ky = 0; ky < 8; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                float2 z = make_float2(fdn_rd(S[ky][kx].x), fdn_rd(S[ky][kx].y));
+                S[ky][kx] = cmul(z, w[ky * 5 + kx]);
+            }
+        irfft2_8x8(S, p);
+    }
+    float ka[9], kb[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { ka[i] = wa[c * 9 + i]; kb[i] = wb[c * 9 + i]; }
+    const bool colL = x0 > 0, colR = x0 + 8 < W;                 // s1 columns -1 and 8 lie inside the image
+    float h0[12], h1[12], h2[12];
+    load_row12(hp, H, W, y0 - 2, x0, h0);
+    load_row12(hp, H, W, y0 - 1, x0, h1);
+#pragma unroll
+    for (int r = -1; r <= 8; ++r) {                              // s1 row r of the patch frame (image row y0 + r)
+        load_row12(hp, H, W, y0 + r + 1, x0, h2);
+        const int gy = y0 + r;
+        if (gy >= 0 && gy < H) {                                 // warp-uniform except where a warp spans two patch rows
+            float s[10];
+#pragma unroll
+            for (int x = 0; x < 10; ++x) {                       // s1 column x - 1; window columns x .. x + 2 of the 12-wide rows
+                float a = ka[0] * h0[x];
+                a += ka[1] * h0[x + 1]; a += ka[2] * h0[x + 2];
+                a += ka[3] * h1[x]; a += ka[4] * h1[x + 1]; a += ka[5] * h1[x + 2];
+                a += ka[6] * h2[x]; a += ka[7] * h2[x + 1]; a += ka[8] * h2[x + 2];
+                s[x] = a;
+            }
+#pragma unroll
+            for (int x = 0; x < 10; x += 2) {
+                const float2 t = fdn_gelu2(make_float2(s[x], s[x + 1]));
+                s[x] = t.x; s[x + 1] = t.y;
+            }
+            if (!colL) s[0] = 0.f;
+            if (!colR) s[9] = 0.f;
+            // scatter: s1 row r is the (dy = r - y + 1) row of output row y, y = r - 1 .. r + 1
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int y = r + 1 - dy;
+                if (y >= 0 && y < 8) {
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        float a = kb[dy * 3] * s[x];
+                        a += kb[dy * 3 + 1] * s[x + 1];
+                        a += kb[dy * 3 + 2] * s[x + 2];
+                        p[8 * y + x] += a;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; }
+    }
+    store_patch(out + off, W, p);
+}
+
 #ifndef FDSA_MIN_BLOCKS
 #define FDSA_MIN_BLOCKS 4
 #endif
@@ -326,106 +427,6 @@ __global__ void __launch_bounds__(128, FDSA_MIN_BLOCKS) k_fdsa_patch_dw(const fl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// FDFFN spatial + spectral branches in one kernel (FDN_arch.py:457-470):
-//     t = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec)
-// A CTA owns a 32x32 pixel tile of 8 channels.  The tile of h (halo 2) is staged in shared memory once; s1 = gelu(dw_a(h))
-// is produced on the 34x34 ring it is needed on (zero outside the image, as the second conv's padding sees it), s2 = dw_b(s1)
-// on the 32x32 tile; then one thread per (channel, 8x8 patch) runs the register FFT on h's centre and adds s2.  Replaces
-// three kernels and five of the seven tensor round trips of the unfused sequence.
-// ---------------------------------------------------------------------------------------------------
-#define FS_T 32
-#define FS_C 8
-#define FS_HP (FS_T + 4)   // h tile edge
-#define FS_SP (FS_T + 2)   // s1 tile edge
-
-__global__ void __launch_bounds__(256, 2) k_fdffn_spatial(const float* __restrict__ h, const float* __restrict__ wa, const float* __restrict__ wb,
-                                                          const float2* __restrict__ wspec, float* __restrict__ out, int C, int H, int W) {
-    FDN_DYN_SMEM(smem);
-    float* sh = reinterpret_cast<float*>(smem);                 // [FS_C][FS_HP][FS_HP]
-    float* s1 = sh + FS_C * FS_HP * FS_HP;                      // [FS_C][FS_SP][FS_SP]
-    float* s2 = s1 + FS_C * FS_SP * FS_SP;                      // [FS_C][FS_T][FS_T]
-    const int tiles_x = (W + FS_T - 1) / FS_T;
-    const int x0 = (blockIdx.x % tiles_x) * FS_T, y0 = (blockIdx.x / tiles_x) * FS_T;
-    const int c0 = blockIdx.y * FS_C, b = blockIdx.z;
-    const int nc = min(FS_C, C - c0);
-    const int tid = threadIdx.x;
-    // ---- stage h with a halo of 2 (zero outside the image)
-    for (int i = tid; i < nc * FS_HP * FS_HP; i += 256) {
-        const int c = i / (FS_HP * FS_HP), r = i - c * (FS_HP * FS_HP);
-        const int yy = r / FS_HP, xx = r - yy * FS_HP;
-        const int gy = y0 + yy - 2, gx = x0 + xx - 2;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = h[(((size_t)b * C + c0 + c) * H + gy) * W + gx];
-        sh[i] = v;
-    }
-    __syncthreads();
-    // ---- s1 = gelu(dw_a(h)) on the 34x34 ring, zero outside the image
-    for (int i = tid; i < nc * FS_SP * FS_SP; i += 256) {
-        const int c = i / (FS_SP * FS_SP), r = i - c * (FS_SP * FS_SP);
-        const int yy = r / FS_SP, xx = r - yy * FS_SP;
-        const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const float* k = wa + (c0 + c) * 9;
-            const float* p = sh + c * FS_HP * FS_HP + yy * FS_HP + xx;     // top-left of the 3x3 window
-            float a = 0.f;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * p[dy * FS_HP + dx];
-            v = fdn_gelu(a);
-        }
-        s1[i] = v;
-    }
-    __syncthreads();
-    // ---- s2 = dw_b(s1) on the tile
-    for (int i = tid; i < nc * FS_T * FS_T; i += 256) {
-        const int c = i / (FS_T * FS_T), r = i - c * (FS_T * FS_T);
-        const int yy = r / FS_T, xx = r - yy * FS_T;
-        const float* k = wb + (c0 + c) * 9;
-        const float* p = s1 + c * FS_SP * FS_SP + yy * FS_SP + xx;
-        float a = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) a += k[dy * 3 + dx] * p[dy * FS_SP + dx];
-        s2[i] = a;
-    }
-    __syncthreads();
-    // ---- spectral branch per (channel, patch) + sum
-    if (tid < nc * 16) {
-        const int c = tid >> 4, pt = tid & 15;
-        const int py = pt >> 2, px = pt & 3;
-        const int gy = y0 + py * 8, gx = x0 + px * 8;
-        if (gy < H && gx < W) {
-            float p[64];
-            float2 S[8][5];
-            const float* src = sh + c * FS_HP * FS_HP + (py * 8 + 2) * FS_HP + px * 8 + 2;
-#pragma unroll
-            for (int y = 0; y < 8; ++y)
-#pragma unroll
-                for (int x = 0; x < 8; ++x) p[8 * y + x] = src[y * FS_HP + x];
-            rfft2_8x8(p, S);
-            const float2* w = wspec + (c0 + c) * 40;
-#pragma unroll
-            for (int ky = 0; ky < 8; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
-                    float2 z = make_float2(fdn_rd(S[ky][kx].x), fdn_rd(S[ky][kx].y));
-                    S[ky][kx] = cmul(z, w[ky * 5 + kx]);
-                }
-            irfft2_8x8(S, p);
-            const float* a2 = s2 + c * FS_T * FS_T + (py * 8) * FS_T + px * 8;
-#pragma unroll
-            for (int y = 0; y < 8; ++y)
-#pragma unroll
-                for (int x = 0; x < 8; ++x) p[8 * y + x] += a2[y * FS_T + x];
-            store_patch(out + (((size_t)b * C + c0 + c) * H + gy) * W + gx, W, p);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 // out = irfft2_8x8( rd(rfft2_8x8(x)) * wspec[c] ) + add.   x, add, out: [B][C][H][W]; wspec: [C][8][5] complex.
@@ -471,18 +472,12 @@ FDN_API int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, 
                               cudaStream_t st) {
     FDN_REQUIRE(h && wa && wb && wspec && out && B > 0 && C > 0, "bad arguments");
     FDN_REQUIRE(H % 8 == 0 && W % 8 == 0, "H and W must be multiples of the 8x8 patch");
-    FDN_REQUIRE(fdn_aligned16(out), "out must be 16-byte aligned");
-    const size_t smem = (size_t)FS_C * (FS_HP * FS_HP + FS_SP * FS_SP + FS_T * FS_T) * sizeof(float);
-    static bool configured[FDN_MAX_DEVICES] = {};
-    const int dev = fdn_device();
-    if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_fdffn_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { fdn_set_error(cudaGetErrorString(e)); return (int)e; }
-        configured[dev] = true;
-    }
-    dim3 grid(fdn_cdiv(W, FS_T) * fdn_cdiv(H, FS_T), fdn_cdiv(C, FS_C), B);
-    FDN_LAUNCH(k_fdffn_spatial, grid, dim3(256), smem, st, h, wa, wb, reinterpret_cast<const float2*>(wspec), out, C, H, W);
-    return fdn_check_launch("k_fdffn_spatial");
+    FDN_REQUIRE(fdn_aligned16(h) && fdn_aligned16(out), "h and out must be 16-byte aligned");
+    FDN_REQUIRE((long long)B * C <= 65535, "too many planes for one launch");
+    const int n = (H / 8) * (W / 8);
+    FDN_LAUNCH_SEQ(k_fdffn_patch_fused, dim3(fdn_cdiv(n, 128), B * C), dim3(128), 0, st, h, wa, wb, reinterpret_cast<const float2*>(wspec), out, C,
+                   H, W, n);
+    return fdn_check_launch("k_fdffn_patch_fused");
 }
 
 // out = irfft2_8x8(rd(rfft2_8x8(h)) * wspec[c]) + depthwise3x3(s1; wb[c])   (FDFFN spectral branch + space.2, FDN_arch.py:439-441,457-470)

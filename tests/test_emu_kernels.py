@@ -57,9 +57,11 @@ def test_emu_fuse(emu):
     P.case_fuse_resample(emu, 32, 8, 8)
 
 
-def test_emu_fdffn_fused_variant(emu, monkeypatch):
-    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_emu_fdffn_fused_variant(emu, monkeypatch, fused):
+    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", fused)
     P.case_tblock(emu, 32, 8, 16, False, False, seed=21)
+    P.case_tblock(emu, 8, 24, 40, False, False, seed=22, b=1)
 
 
 def test_emu_image_pre_post(emu):

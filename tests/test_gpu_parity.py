@@ -310,11 +310,14 @@ def test_ffma_path_still_matches(cuda_dev, monkeypatch):
     P.case_fuse_resample(cuda_dev, 32, 16, 24)
 
 
-def test_fdffn_fused_variant(cuda_dev, monkeypatch):
-    """Opt-in fused FDFFN middle section (dw-GELU-dw + patch FFT + sum in one kernel) against the fp64 oracle."""
-    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", "1")
-    P.case_tblock(cuda_dev, 32, 40, 72, False, False, seed=21)      # ragged 32x32 tiles
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_fdffn_fused_variant(cuda_dev, monkeypatch, fused):
+    """FDFFN middle section: the fused per-patch kernel (dw-GELU-dw + patch FFT + sum, the default) and the two-kernel form
+    (FDN_B200_FDFFN_FUSED=0) against the fp64 oracle, on sizes whose patch rows wrap inside a warp."""
+    monkeypatch.setenv("FDN_B200_FDFFN_FUSED", fused)
+    P.case_tblock(cuda_dev, 32, 40, 72, False, False, seed=21)
     P.case_tblock(cuda_dev, 64, 32, 32, False, False, seed=22)
+    P.case_tblock(cuda_dev, 24, 8, 8, False, False, seed=23)        # a single patch: every halo element is image border
 
 
 def test_image_pre_post_bit_exact(cuda_dev):
