@@ -209,13 +209,18 @@ __device__ __forceinline__ const float* src_row(const PwMmaParams& q, int b, int
 // store (out may alias res for in-place residuals); null pointers switch a stage off in the generic instantiation, offsets stay 32-bit (16 planes * HW * 4 B < 2^31 for any image we accept).
 template <bool FULL, bool RES, bool FILM, bool BIAS>
 __device__ __forceinline__ void epi_group(float (&acc)[16], float* op, const float* rp, const float* fm, const float* fa,
-                                          const float* bias, const float (&rpre)[16], bool pre, float res_coef, uint32_t HW, int nvalid) {
+                                          const float* bias, const float (&rpre)[16], bool pre, float res_coef, uint32_t HW, int nvalid,
+                                          const float* fmpre = nullptr, const float* fapre = nullptr) {
     if (BIAS && bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if (FULL || j < nvalid) acc[j] += bias[j];
     }
-    if (FILM && fm != nullptr) {
+    if (FILM && fmpre != nullptr) {                    // FiLM maps fetched before the accumulator wait (registers)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (FULL || j < nvalid) acc[j] = acc[j] * fmpre[j] + fapre[j];
+    } else if (FILM && fm != nullptr) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if (FULL || j < nvalid) acc[j] = acc[j] * fm[(size_t)HW * j] + fa[(size_t)HW * j];
@@ -716,6 +721,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
             const uint32_t buf = q.nbuf == 2 ? (titer & 1) : 0;
             const uint32_t use = q.nbuf == 2 ? (titer >> 1) : titer;
             const uint32_t tacc = tlane + buf * set_cols;
+            // FiLM maps of this warp's first 16-column group: independent of the accumulator, so they are requested BEFORE the wait for
+            // the MMAs of the tile - their HBM latency overlaps the wait instead of following it (ncu: long_scoreboard 8.5 on the
+            // FCAFFN project_in shapes)
+            float fmv[16], fav[16];
+            const bool film_pre = has_film && valid && c16_begin < c16_end && nfirst >= 16;
+            if (film_pre) {
+                const size_t g0 = base + (size_t)HWu * (uint32_t)(c16_begin * 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { fmv[j] = q.film_mul[g0 + (size_t)HWu * j]; fav[j] = q.film_add[g0 + (size_t)HWu * j]; }
+            }
             mbar_wait_t(&acc_full[buf], use & 1, &w0, rec);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int c16 = c16_begin; c16 < c16_end; ++c16) {
@@ -757,7 +772,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) k_pw_mma(PwMmaParams q) {
                         const float* fm = has_film ? q.film_mul + goff : nullptr;
                         const float* fa = has_film ? q.film_add + goff : nullptr;
                         // generic: null-guarded (rpre is zero when there is no residual)
-                        epi_group<false, true, true, true>(acc, out_p + goff, has_res ? res_p + goff : nullptr, fm, fa, bn, rnext, pre, res_coef, HWu, min(nvalid, 16));
+                        const bool fpre = film_pre && c16 == c16_begin;
+                        epi_group<false, true, true, true>(acc, out_p + goff, has_res ? res_p + goff : nullptr, fm, fa, bn, rnext, pre, res_coef, HWu, min(nvalid, 16),
+                                                           fpre ? fmv : nullptr, fpre ? fav : nullptr);
                     }
                 }
                 // the prefetched residual has been consumed: refill the same registers for the next tile of this CTA
