@@ -70,7 +70,8 @@ int fdn_fdffn_patch_dw(const float* h, const float* s1, const float* wb, const f
                        cudaStream_t st);
 
 /* FDFFN middle section fused (FDN_arch.py:457-470): out = dw_b(gelu(dw_a(h))) + irfft2_8x8(rd(rfft2_8x8(h)) * wspec);
- * wa, wb [C][9] = space.0 / space.2 depthwise weights. */
+ * wa, wb [C][9] = space.0 / space.2 depthwise weights.  One thread per (channel, 8x8 patch); the intermediate gelu(dw_a(h)) is
+ * produced row by row in registers (zero outside the image, as dw_b's padding sees it) and never written to memory. */
 int fdn_fdffn_spatial(const float* h, const float* wa, const float* wb, const float* wspec, float* out, int B, int C, int H, int W,
                       cudaStream_t st);
 
