@@ -67,22 +67,35 @@ __device__ __forceinline__ float fdn_rcp_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float fdn_ex2_fast(float x) {           // 2^x, one MUFU
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 #define FDN_EXPF(x) fdn_exp_fast(x)
 #endif
+#ifdef FDN_EMU
+__device__ __forceinline__ float fdn_ex2_fast(float x) { return exp2f(x); }
+#endif
+// GELU works on u = |x| sqrt(log2 e) / sqrt 2 so that e^{-z^2} = 2^{-u^2} needs no pre-scaling: z = u / sqrt(log2 e)
+#define FDN_GELU_KU 0.8493218002880191f      /* sqrt(log2 e) / sqrt 2 */
+#define FDN_GELU_K39 0.32469629835150216f    /* 0.39 / sqrt(log2 e) */
+#define FDN_GELU_KH (-0.5887050112577373f)   /* -1 / (sqrt 2 sqrt(log2 e)):  KH u = -0.5 |x| */
 // erf-form GELU (F.gelu default): 0.5 x (1 + erf(x / sqrt 2)), evaluated through erfc(z) = t P(t) e^{-z^2}, t = 1/(1 + 0.39 z), z = |x| / sqrt 2
-// (degree-6 fit, |error| < 2e-8 before rounding).  Writing 1 + erf as 2 - erfc / erfc keeps small results of negative arguments
-// free of cancellation.  In fp32 its error equals the erff() formulation's (max 3.8e-7 / rms 6.1e-8 vs 4.5e-7 / 6.8e-8 over [-8, 8])
+// (degree-6 fit, |error| < 2e-8 before rounding).  The result is formed as relu(x) - 0.5 |x| erfc(z), which keeps small results of
+// negative arguments free of cancellation (there it is just -0.5 |x| erfc(z)).  In fp32 its error equals the erff() formulation's (max 3.8e-7 / rms 6.1e-8 vs 4.5e-7 / 6.8e-8 over [-8, 8])
 // at about half the instructions: two MUFU (rcp, ex2) and ten FMA-pipe operations.
 __device__ __forceinline__ float fdn_gelu(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = fdn_rcp_fast(fmaf(0.39f, z, 1.0f));
+    const float u = fabsf(x) * FDN_GELU_KU;
+    const float t = fdn_rcp_fast(fmaf(FDN_GELU_K39, u, 1.0f));
     float q = fmaf(-2.280578155e-01f, t, 8.887884326e-01f);
     q = fmaf(q, t, -6.388445279e-01f);
     q = fmaf(q, t, 6.523336912e-01f);
     q = fmaf(q, t, 9.027867826e-02f);
     q = fmaf(q, t, 2.355015248e-01f);
-    const float ec = q * t * FDN_EXPF(-z * z);              // erfc(z)
-    return 0.5f * x * (x >= 0.f ? 2.0f - ec : ec);
+    const float ec = q * t * fdn_ex2_fast(-u * u);             // erfc(z)
+    // 0.5 x (2 - erfc) for x >= 0 and 0.5 x erfc for x < 0 are both  relu(x) - 0.5 |x| erfc(z): no select, one rounding fewer
+    return fmaf(u * FDN_GELU_KH, ec, fmaxf(x, 0.f));
 }
 // ---- packed fp32x2 helpers (Blackwell FMUL2 / FFMA2; scalar forms in the emulation build, bit-identical) ----------------------------
 // A scalar operand written as the pair {s, s} is encoded by ptxas as a broadcast register operand (no move).
@@ -127,8 +140,8 @@ __device__ __forceinline__ float2 f2fma_c(float2 a, float2 b, float c) {   // a*
 // gelu of two values at once (and gelu(g) * l below): the same operation sequence as fdn_gelu (bit-identical), the polynomial and the
 // products packed
 __device__ __forceinline__ float2 fdn_gelu2(float2 g) {
-    const float2 z = make_float2(fabsf(g.x) * 0.70710678118654752440f, fabsf(g.y) * 0.70710678118654752440f);
-    const float2 den = f2fma_c(make_float2(0.39f, 0.39f), z, 1.0f);
+    const float2 z = make_float2(fabsf(g.x) * FDN_GELU_KU, fabsf(g.y) * FDN_GELU_KU);          // u of fdn_gelu
+    const float2 den = f2fma_c(make_float2(FDN_GELU_K39, FDN_GELU_K39), z, 1.0f);
     const float2 t = make_float2(fdn_rcp_fast(den.x), fdn_rcp_fast(den.y));
     float2 q = f2fma_c(make_float2(-2.280578155e-01f, -2.280578155e-01f), t, 8.887884326e-01f);
     q = f2fma_c(q, t, -6.388445279e-01f);
@@ -136,14 +149,13 @@ __device__ __forceinline__ float2 fdn_gelu2(float2 g) {
     q = f2fma_c(q, t, 9.027867826e-02f);
     q = f2fma_c(q, t, 2.355015248e-01f);
     const float2 nz2 = f2mul(make_float2(-z.x, -z.y), z);
-    const float2 e = make_float2(FDN_EXPF(nz2.x), FDN_EXPF(nz2.y));
+    const float2 e = make_float2(fdn_ex2_fast(nz2.x), fdn_ex2_fast(nz2.y));
     const float2 ec = f2mul(f2mul(q, t), e);
-    const float2 sel = make_float2(g.x >= 0.f ? 2.0f - ec.x : ec.x, g.y >= 0.f ? 2.0f - ec.y : ec.y);
-    return f2mul(f2mul_s(g, 0.5f), sel);
+    return f2fma(f2mul_s(z, FDN_GELU_KH), ec, make_float2(fmaxf(g.x, 0.f), fmaxf(g.y, 0.f)));     // relu(g) - 0.5 |g| erfc(z)
 }
 __device__ __forceinline__ float2 fdn_gelu_gate2(float2 g, float2 l) {
-    const float2 z = make_float2(fabsf(g.x) * 0.70710678118654752440f, fabsf(g.y) * 0.70710678118654752440f);
-    const float2 den = f2fma_c(make_float2(0.39f, 0.39f), z, 1.0f);
+    const float2 z = make_float2(fabsf(g.x) * FDN_GELU_KU, fabsf(g.y) * FDN_GELU_KU);          // u of fdn_gelu
+    const float2 den = f2fma_c(make_float2(FDN_GELU_K39, FDN_GELU_K39), z, 1.0f);
     const float2 t = make_float2(fdn_rcp_fast(den.x), fdn_rcp_fast(den.y));
     float2 q = f2fma_c(make_float2(-2.280578155e-01f, -2.280578155e-01f), t, 8.887884326e-01f);
     q = f2fma_c(q, t, -6.388445279e-01f);
@@ -151,10 +163,9 @@ __device__ __forceinline__ float2 fdn_gelu_gate2(float2 g, float2 l) {
     q = f2fma_c(q, t, 9.027867826e-02f);
     q = f2fma_c(q, t, 2.355015248e-01f);
     const float2 nz2 = f2mul(make_float2(-z.x, -z.y), z);
-    const float2 e = make_float2(FDN_EXPF(nz2.x), FDN_EXPF(nz2.y));
+    const float2 e = make_float2(fdn_ex2_fast(nz2.x), fdn_ex2_fast(nz2.y));
     const float2 ec = f2mul(f2mul(q, t), e);
-    const float2 sel = make_float2(g.x >= 0.f ? 2.0f - ec.x : ec.x, g.y >= 0.f ? 2.0f - ec.y : ec.y);
-    return f2mul(f2mul(f2mul_s(g, 0.5f), sel), l);
+    return f2mul(f2fma(f2mul_s(z, FDN_GELU_KH), ec, make_float2(fmaxf(g.x, 0.f), fmaxf(g.y, 0.f))), l);
 }
 __device__ __forceinline__ float fdn_lrelu(float x) { return x > 0.f ? x : 0.1f * x; }
 __device__ __forceinline__ float fdn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }

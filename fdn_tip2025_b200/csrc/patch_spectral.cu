@@ -289,33 +289,43 @@ __global__ void __launch_bounds__(128, 3) k_fdffn_patch_fused(const float* __res
         load_row12(hp, H, W, y0 + r + 1, x0, h2);
         const int gy = y0 + r;
         if (gy >= 0 && gy < H) {                                 // warp-uniform except where a warp spans two patch rows
+            // Two adjacent outputs per packed operation: the rows sit in even-aligned register pairs (that is how the 64- / 128-bit loads
+            // deliver them), so for an even output column x the taps dx = 0 and dx = 2 read the aligned pairs (h[x], h[x+1]) and
+            // (h[x+2], h[x+3]) - one FFMA2 each with the weight as a broadcast operand - and only the dx = 1 taps, whose pair would
+            // straddle two register pairs, stay scalar: 12 instead of 18 issue slots per output pair, no operand moves.
+            float2 s2[5];                                        // (s1 column 2i - 1, s1 column 2i)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int x = 2 * i;
+                float2 a = f2mul_s(make_float2(h0[x], h0[x + 1]), ka[0]);
+                a = cfma(make_float2(h0[x + 2], h0[x + 3]), ka[2], a);
+                a = cfma(make_float2(h1[x], h1[x + 1]), ka[3], a);
+                a = cfma(make_float2(h1[x + 2], h1[x + 3]), ka[5], a);
+                a = cfma(make_float2(h2[x], h2[x + 1]), ka[6], a);
+                a = cfma(make_float2(h2[x + 2], h2[x + 3]), ka[8], a);
+                a.x = fmaf(ka[1], h0[x + 1], a.x); a.y = fmaf(ka[1], h0[x + 2], a.y);
+                a.x = fmaf(ka[4], h1[x + 1], a.x); a.y = fmaf(ka[4], h1[x + 2], a.y);
+                a.x = fmaf(ka[7], h2[x + 1], a.x); a.y = fmaf(ka[7], h2[x + 2], a.y);
+                s2[i] = fdn_gelu2(a);
+            }
             float s[10];
 #pragma unroll
-            for (int x = 0; x < 10; ++x) {                       // s1 column x - 1; window columns x .. x + 2 of the 12-wide rows
-                float a = ka[0] * h0[x];
-                a += ka[1] * h0[x + 1]; a += ka[2] * h0[x + 2];
-                a += ka[3] * h1[x]; a += ka[4] * h1[x + 1]; a += ka[5] * h1[x + 2];
-                a += ka[6] * h2[x]; a += ka[7] * h2[x + 1]; a += ka[8] * h2[x + 2];
-                s[x] = a;
-            }
-#pragma unroll
-            for (int x = 0; x < 10; x += 2) {
-                const float2 t = fdn_gelu2(make_float2(s[x], s[x + 1]));
-                s[x] = t.x; s[x + 1] = t.y;
-            }
+            for (int i = 0; i < 5; ++i) { s[2 * i] = s2[i].x; s[2 * i + 1] = s2[i].y; }
             if (!colL) s[0] = 0.f;
             if (!colR) s[9] = 0.f;
-            // scatter: s1 row r is the (dy = r - y + 1) row of output row y, y = r - 1 .. r + 1
+            // scatter: s1 row r is the (dy = r - y + 1) row of output row y, y = r - 1 .. r + 1; same pairing for the output columns
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
                 const int y = r + 1 - dy;
                 if (y >= 0 && y < 8) {
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) {
-                        float a = kb[dy * 3] * s[x];
-                        a += kb[dy * 3 + 1] * s[x + 1];
-                        a += kb[dy * 3 + 2] * s[x + 2];
-                        p[8 * y + x] += a;
+                    for (int x = 0; x < 8; x += 2) {
+                        float2 a = make_float2(p[8 * y + x], p[8 * y + x + 1]);
+                        a = cfma(make_float2(s[x], s[x + 1]), kb[dy * 3], a);
+                        a = cfma(make_float2(s[x + 2], s[x + 3]), kb[dy * 3 + 2], a);
+                        a.x = fmaf(kb[dy * 3 + 1], s[x + 1], a.x);
+                        a.y = fmaf(kb[dy * 3 + 1], s[x + 2], a.y);
+                        p[8 * y + x] = a.x; p[8 * y + x + 1] = a.y;
                     }
                 }
             }
