@@ -197,6 +197,12 @@ def case_pw_conv(dev):
         ops.pw_conv([(dev32(s0, dev), 0)], dev32(wgt[:, :5].t(), dev), out)
         sync(dev)
         compare("pw_conv small N=%d plain" % n, out, F.conv2d(s0.float().double(), wgt[:, :5].float().double()[:, :, None, None]), rel_l2=2e-6, max_rel=5e-6)
+    # width not a multiple of four: the few-output kernel does not apply, the tiled kernel must take over
+    xo, wgt = rnd(b, 6, 5, 18, seed=30), rnd(12, 6, seed=31)
+    out = torch.empty(b, 12, 5, 18, device=dev)
+    ops.pw_conv([(dev32(xo, dev), 0)], dev32(wgt.t(), dev), out)
+    sync(dev)
+    compare("pw_conv N=12, W=18", out, F.conv2d(xo.float().double(), wgt.float().double()[:, :, None, None]), rel_l2=2e-6, max_rel=5e-6)
 
 
 def case_conv2d(dev):

@@ -41,6 +41,8 @@ def test_emu_fft_fast_and_prime_first(emu):
     P.case_rfft2_irfft2(emu, 64, 64, planes=1)        # register-pipeline kernels (fft_fast.cuh)
     P.case_rfft2_irfft2(emu, 46, 94, planes=1)        # 46 = 2*23, 47: prime radices first, no input twiddles
     P.case_rfft2_irfft2(emu, 58, 1334, planes=1)      # 667 = 23*29: first-pass and general prime passes in one transform
+    P.case_rfft2_irfft2(emu, 24, 64, planes=1)        # 24 rows, 16 rows per CTA: the non-persistent row kernels (no whole tiles)
+    P.case_rfft2_irfft2(emu, 160, 64, planes=3)       # persistent TMA-staged rows looping over several tiles per CTA, 16-column tiles
 
 
 def test_emu_pointwise_and_convs(emu):
